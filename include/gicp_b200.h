@@ -1,0 +1,155 @@
+/* gicp_b200.h - C ABI of libgicp_b200.so, a B200 (sm_100a) GICP registration engine.
+ *
+ * This is the drop-in boundary for ONE path of catec/leica_point_cloud_processing: fine registration
+ * behind `GICPAlignment` and the nearest-distance cloud difference behind `Filter::removeFromCloud`.
+ * Each entry point names the reference interface it replaces (paths relative to the reference root).
+ * The reference has no FFI layer (it is a plain C++ class linked against PCL), so the "binding" a
+ * maintainer adds is the header-only C++ shim include/GICPAlignment_b200.hpp; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch / PCL types cross this boundary
+ *   - every function returns GICPB_OK (0) or a negative GICPB_E_* code; gicpb_last_error(ctx) holds text
+ *   - clouds are given as a base pointer to the first x, a point count and a byte stride between points
+ *     (x, y, z are three consecutive float32).  stride 32 = pcl::PointXYZRGB as the reference holds it
+ *     (include/GICPAlignment.h:35), stride 16 = float4, stride 12 = packed xyz
+ *   - `on_device` != 0 means the pointer is a CUDA device pointer on the context's GPU; otherwise host
+ *   - 4x4 transforms are float32, ROW-major (T[4*r + c]); Eigen::Matrix4f is column-major, the shim transposes
+ *   - a context is bound to one GPU and is not thread-safe; distinct contexts are independent
+ *   - there is no CPU fallback: without a usable GPU gicpb_create fails with GICPB_E_CUDA
+ */
+#ifndef GICP_B200_H_
+#define GICP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GICPB_OK 0
+#define GICPB_E_BADARG (-1)
+#define GICPB_E_CUDA (-2)
+#define GICPB_E_NCCL (-3)
+#define GICPB_E_NOT_ENOUGH_CORRESPONDENCES (-4) /* PCL NotEnoughPointsException: < 4 pairs            */
+#define GICPB_E_SOLVER (-5)                     /* PCL SolverDidntConvergeException                     */
+#define GICPB_E_STATE (-6)                      /* call order: clouds / covariances missing             */
+#define GICPB_E_TOO_FEW_POINTS (-7)             /* k_correspondences > cloud size (gicp.hpp)            */
+
+typedef struct gicpb_ctx gicpb_ctx;
+
+/* Parameters of pcl::GeneralizedIterativeClosestPoint that the reference sets or inherits.
+ * Defaults = reference src/GICPAlignment.cpp:29-32 over the PCL 1.8.1 gicp.h defaults. */
+typedef struct gicpb_params {
+  int max_iterations;             /* setMaximumIterations          src/GICPAlignment.cpp:50   (100)   */
+  double transformation_epsilon;  /* setTransformationEpsilon      src/GICPAlignment.cpp:52   (4e-3)  */
+  double rotation_epsilon;        /* PCL rotation_epsilon_                                    (2e-3)  */
+  double max_corr_distance;       /* setMaxCorrespondenceDistance  src/GICPAlignment.cpp:51   (4e-2)  */
+  int k_correspondences;          /* PCL k_correspondences_ (2..32)                           (20)    */
+  double gicp_epsilon;            /* PCL gicp_epsilon_                                        (1e-3)  */
+  int max_inner_iterations;       /* PCL max_inner_iterations_                                (20)    */
+  /* engine knobs (no reference counterpart; results do not depend on them) */
+  float cell_size;                /* uniform-grid cell edge in metres; <= 0 -> chosen from point density */
+  float points_per_cell;          /* density target when cell_size <= 0                       (3.0)   */
+  int mahalanobis_fp32;           /* 0: store M as 6 doubles (default); 1: 6 floats (56 B/pair cost pass) */
+  int use_previous_match;         /* 1 (default): seed each NN search with last iteration's match     */
+} gicpb_params;
+
+typedef struct gicpb_align_result {
+  float transform[16];       /* getFinalTransformation()  src/GICPAlignment.cpp:104, row-major         */
+  int converged;             /* hasConverged()            src/GICPAlignment.cpp:101                    */
+  int status;                /* GICPB_OK or the GICPB_E_* that ended the outer loop                    */
+  int outer_iterations;      /* nr_iterations_                                                         */
+  int inner_iterations;      /* BFGS steps summed over the outer loop                                  */
+  int64_t cost_evaluations;  /* cost/gradient kernel launches                                          */
+  int64_t corr_queries;      /* source queries processed by the correspondence kernel (all outer its.) */
+  int64_t corr_pairs_last;   /* correspondences of the last outer iteration (all ranks)                */
+  double ms_total;           /* wall ms of gicpb_align                                                 */
+  double ms_corr;            /* device ms in the correspondence (NN + gate + Mahalanobis) kernel       */
+  double ms_cost;            /* device ms in the cost/gradient kernel                                  */
+} gicpb_align_result;
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+void gicpb_default_params(gicpb_params* p);
+int gicpb_create(int device, gicpb_ctx** out);                 /* ctor  src/GICPAlignment.cpp:23-35    */
+void gicpb_destroy(gicpb_ctx* ctx);                            /* dtor  include/GICPAlignment.h:53     */
+const char* gicpb_last_error(const gicpb_ctx* ctx);
+int gicpb_set_params(gicpb_ctx* ctx, const gicpb_params* p);   /* configParameters :48-54              */
+int gicpb_get_params(const gicpb_ctx* ctx, gicpb_params* p);
+
+/* ---- multi-GPU: one process per GPU, source points sharded by rank, target replicated --------------
+ * The per-evaluation partial sums are all-reduced with NCCL (ncclAllReduce, 14 doubles).  NCCL is
+ * dlopen'ed from `libnccl_path` (NULL: "libnccl.so.2"), so the library has no link-time NCCL dependency. */
+int gicpb_nccl_unique_id(const char* libnccl_path, unsigned char id_out[128]);
+int gicpb_comm_init(gicpb_ctx* ctx, const char* libnccl_path, int rank, int world, const unsigned char id[128]);
+int gicpb_comm_rank(const gicpb_ctx* ctx, int* rank, int* world);
+
+/* ---- clouds: upload once, index on the GPU (replaces setInputTarget / setInputSource and the two FLANN
+ *      kd-tree builds, src/GICPAlignment.cpp:89-90; PCL Registration::initCompute[Reciprocal]) ------- */
+int gicpb_set_target(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
+int gicpb_set_source(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
+/* kNN-k covariances of both clouds, regularised to (1, 1, gicp_epsilon) (PCL GICP::computeCovariances).
+ * Called implicitly by gicpb_align when missing; cached until the cloud is set again (PCL A.1 semantics). */
+int gicpb_compute_covariances(gicpb_ctx* ctx);
+
+/* ---- the solve (replaces gicp_.align(), src/GICPAlignment.cpp:96,116; guess = identity as there) ---- */
+int gicpb_align(gicpb_ctx* ctx, gicpb_align_result* out);
+/* getFitnessScore(max_range) under `transform` (src/GICPAlignment.cpp:103,123); all ranks get the value */
+int gicpb_fitness(gicpb_ctx* ctx, const float transform[16], double max_range, double* score);
+
+/* ---- pcl::transformPointCloud (src/GICPAlignment.cpp:146, src/LeicaStateMachine.cpp:182): xyz of every
+ *      point is replaced by T * xyz, all other bytes of the stride are copied.  in == out is allowed. -- */
+int gicpb_transform_cloud(gicpb_ctx* ctx, const float transform[16], const void* in, void* out, int64_t n,
+                          int64_t stride_bytes, int on_device);
+
+/* ---- Filter::removeFromCloud (src/Filter.cpp:176-189 -> pcl::getPointCloudDifference): mask[i] = 1 iff
+ *      input point i is finite and its squared NN distance in `subtract` is > sqr_threshold.
+ *      n_kept may be NULL.  Does not touch the clouds set for alignment. ----------------------------- */
+int gicpb_cloud_difference(gicpb_ctx* ctx, const void* input, int64_t n_input, int64_t input_stride,
+                           const void* subtract, int64_t n_subtract, int64_t subtract_stride, int on_device,
+                           double sqr_threshold, uint8_t* mask, int64_t* n_kept);
+/* Two-step form for repeated differences against one cloud (index built once). */
+int gicpb_difference_set_subtract(gicpb_ctx* ctx, const void* subtract, int64_t n, int64_t stride, int on_device);
+int gicpb_difference_run(gicpb_ctx* ctx, const void* input, int64_t n, int64_t stride, int on_device,
+                         double sqr_threshold, uint8_t* mask, int mask_on_device, int64_t* n_kept);
+
+/* ---- test / inspection hooks (parity checks against the oracle) ------------------------------------- */
+/* exact NN-1 of `n` queries in the target: idx = ORIGINAL target index (-1: none), d2 = float32 squared
+ * distance.  max_dist <= 0 -> ungated; else only neighbours with d2 < max_dist^2 (strict) are reported. */
+int gicpb_nn1(gicpb_ctx* ctx, const void* queries, int64_t n, int64_t stride_bytes, int on_device,
+              const float transform[16], double max_dist, int32_t* idx, float* d2);
+/* self-kNN of the target (which = 0) or source (which = 1) cloud, k = params.k_correspondences, rows in
+ * ORIGINAL point order, neighbours sorted by (d2, index); idx/d2 are host arrays of n*k. */
+int gicpb_knn(gicpb_ctx* ctx, int which, int32_t* idx, float* d2);
+/* regularised covariances (row-major 3x3 doubles, ORIGINAL point order, host array of 9*n). */
+int gicpb_get_covariances(gicpb_ctx* ctx, int which, double* cov9);
+/* correspondences + Mahalanobis matrices of one outer iteration under `transform`: host arrays in ORIGINAL
+ * source order (this rank's shard only when sharded): nn_idx (-1 = gated out), d2, maha9 (9 doubles each). */
+int gicpb_correspondences(gicpb_ctx* ctx, const float transform[16], int32_t* nn_idx, float* d2, double* maha9,
+                          int64_t* n_pairs);
+/* one evaluation of the objective for the correspondences of the last gicpb_correspondences / align
+ * iteration at x = (tx,ty,tz,roll,pitch,yaw): f and g[6] as PCL's OptimizationFunctorWithIndices::fdf */
+int gicpb_cost(gicpb_ctx* ctx, const double x[6], double* f, double g[6]);
+/* grid statistics of a cloud index: which = 0 target, 1 source, 2 subtract */
+typedef struct gicpb_grid_info {
+  int64_t n_points, n_indexed;
+  float cell_size;
+  int dims[3];
+  int64_t n_bricks_occupied, n_cells_occupied;
+  double ms_build;
+} gicpb_grid_info;
+int gicpb_grid_info_get(gicpb_ctx* ctx, int which, gicpb_grid_info* out);
+
+/* ---- micro-benchmark hooks: run one kernel `iters` times on resident data, return mean device ms ----
+ * which: 0 = correspondence pass (NN + gate + Mahalanobis) under `transform`
+ *        1 = cost/gradient evaluation at x derived from `transform`
+ *        2 = NN-1 only (no Mahalanobis build)                                                           */
+int gicpb_bench_kernel(gicpb_ctx* ctx, int which, const float transform[16], int iters, double* ms_mean,
+                       int64_t* launches);
+/* number of kernels this library launched since the context was created */
+int64_t gicpb_launch_count(const gicpb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GICP_B200_H_ */

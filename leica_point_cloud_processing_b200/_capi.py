@@ -1,0 +1,364 @@
+"""ctypes binding of libgicp_b200.so (C ABI declared in include/gicp_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 GPU is usable, loading / creating a
+context raises.  PyTorch is not needed by this module; tensors can be passed by device pointer.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libgicp_b200.so")
+
+GICPB_OK = 0
+E_BADARG, E_CUDA, E_NCCL, E_NOT_ENOUGH_CORRESPONDENCES, E_SOLVER, E_STATE, E_TOO_FEW_POINTS = -1, -2, -3, -4, -5, -6, -7
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int32_p = ctypes.POINTER(ctypes.c_int32)
+c_int64_p = ctypes.POINTER(ctypes.c_int64)
+c_uint8_p = ctypes.POINTER(ctypes.c_uint8)
+
+
+class Params(ctypes.Structure):
+    """gicpb_params; defaults = reference src/GICPAlignment.cpp:29-32 over PCL 1.8.1 gicp.h defaults."""
+    _fields_ = [
+        ("max_iterations", ctypes.c_int),
+        ("transformation_epsilon", ctypes.c_double),
+        ("rotation_epsilon", ctypes.c_double),
+        ("max_corr_distance", ctypes.c_double),
+        ("k_correspondences", ctypes.c_int),
+        ("gicp_epsilon", ctypes.c_double),
+        ("max_inner_iterations", ctypes.c_int),
+        ("cell_size", ctypes.c_float),
+        ("points_per_cell", ctypes.c_float),
+        ("mahalanobis_fp32", ctypes.c_int),
+        ("use_previous_match", ctypes.c_int),
+    ]
+
+
+class AlignResult(ctypes.Structure):
+    _fields_ = [
+        ("transform", ctypes.c_float * 16),
+        ("converged", ctypes.c_int),
+        ("status", ctypes.c_int),
+        ("outer_iterations", ctypes.c_int),
+        ("inner_iterations", ctypes.c_int),
+        ("cost_evaluations", ctypes.c_int64),
+        ("corr_queries", ctypes.c_int64),
+        ("corr_pairs_last", ctypes.c_int64),
+        ("ms_total", ctypes.c_double),
+        ("ms_corr", ctypes.c_double),
+        ("ms_cost", ctypes.c_double),
+    ]
+
+
+class GridInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_points", ctypes.c_int64),
+        ("n_indexed", ctypes.c_int64),
+        ("cell_size", ctypes.c_float),
+        ("dims", ctypes.c_int * 3),
+        ("n_bricks_occupied", ctypes.c_int64),
+        ("n_cells_occupied", ctypes.c_int64),
+        ("ms_build", ctypes.c_double),
+    ]
+
+
+# every symbol include/gicp_b200.h declares: (name, restype, argtypes)
+_VOID_P = ctypes.c_void_p
+_SIGNATURES = [
+    ("gicpb_default_params", None, [ctypes.POINTER(Params)]),
+    ("gicpb_create", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_VOID_P)]),
+    ("gicpb_destroy", None, [_VOID_P]),
+    ("gicpb_last_error", ctypes.c_char_p, [_VOID_P]),
+    ("gicpb_set_params", ctypes.c_int, [_VOID_P, ctypes.POINTER(Params)]),
+    ("gicpb_get_params", ctypes.c_int, [_VOID_P, ctypes.POINTER(Params)]),
+    ("gicpb_nccl_unique_id", ctypes.c_int, [ctypes.c_char_p, c_uint8_p]),
+    ("gicpb_comm_init", ctypes.c_int, [_VOID_P, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, c_uint8_p]),
+    ("gicpb_comm_rank", ctypes.c_int, [_VOID_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    ("gicpb_set_target", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    ("gicpb_set_source", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    ("gicpb_compute_covariances", ctypes.c_int, [_VOID_P]),
+    ("gicpb_align", ctypes.c_int, [_VOID_P, ctypes.POINTER(AlignResult)]),
+    ("gicpb_fitness", ctypes.c_int, [_VOID_P, c_float_p, ctypes.c_double, c_double_p]),
+    ("gicpb_transform_cloud", ctypes.c_int, [_VOID_P, c_float_p, _VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64,
+                                             ctypes.c_int]),
+    ("gicpb_cloud_difference", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, _VOID_P, ctypes.c_int64,
+                                              ctypes.c_int64, ctypes.c_int, ctypes.c_double, _VOID_P, c_int64_p]),
+    ("gicpb_difference_set_subtract", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    ("gicpb_difference_run", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                            ctypes.c_double, _VOID_P, ctypes.c_int, c_int64_p]),
+    ("gicpb_nn1", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, c_float_p,
+                                 ctypes.c_double, c_int32_p, c_float_p]),
+    ("gicpb_knn", ctypes.c_int, [_VOID_P, ctypes.c_int, c_int32_p, c_float_p]),
+    ("gicpb_get_covariances", ctypes.c_int, [_VOID_P, ctypes.c_int, c_double_p]),
+    ("gicpb_correspondences", ctypes.c_int, [_VOID_P, c_float_p, c_int32_p, c_float_p, c_double_p, c_int64_p]),
+    ("gicpb_cost", ctypes.c_int, [_VOID_P, c_double_p, c_double_p, c_double_p]),
+    ("gicpb_grid_info_get", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.POINTER(GridInfo)]),
+    ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
+    ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
+]
+EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+
+_lib = None
+
+
+def load_library():
+    """Load libgicp_b200.so (built in-tree by `make -C leica_point_cloud_processing_b200/csrc` or
+    __graft_entry__.build()).  Raises if it is missing: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `make -C {os.path.join(_PKG_DIR, 'csrc')}` "
+            "(or __graft_entry__.build()); this package has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, restype, argtypes in _SIGNATURES:
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+class GicpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgicp_b200 error {code}: {msg}")
+        self.code = code
+
+
+def find_libnccl():
+    """Path of the NCCL library torch ships (so the engine and torch.distributed share one libnccl)."""
+    try:
+        import nvidia.nccl  # noqa: F401
+        for d in list(nvidia.nccl.__path__):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def _as_cloud(a):
+    """Return (keepalive, pointer, n, stride_bytes, on_device) for a numpy array [n, >=3] float32 (any row stride),
+    a structured/byte numpy array of 32-byte points, or a CUDA torch tensor [n, 3|4|8] float32."""
+    if hasattr(a, "is_cuda"):  # torch tensor
+        if a.dtype.is_floating_point is False or a.element_size() != 4:
+            raise TypeError("cloud tensor must be float32")
+        if a.dim() != 2 or a.shape[1] < 3 or a.stride(1) != 1:
+            raise TypeError("cloud tensor must be [n, >=3] with unit inner stride")
+        return a, a.data_ptr(), int(a.shape[0]), int(a.stride(0)) * 4, 1 if a.is_cuda else 0
+    a = np.asarray(a)
+    if a.dtype != np.float32:
+        a = a.astype(np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise TypeError("cloud array must be [n, >=3] float32")
+    if a.strides[1] != 4 or a.strides[0] % 4 != 0 or a.strides[0] < 12:
+        a = np.ascontiguousarray(a)
+    return a, a.ctypes.data, int(a.shape[0]), int(a.strides[0]), 0
+
+
+def _T(T):
+    T = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(4, 4))
+    return T, T.ctypes.data_as(c_float_p)
+
+
+class Engine:
+    """Thin object wrapper over one gicpb_ctx."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _VOID_P()
+        rc = self.lib.gicpb_create(int(device), ctypes.byref(h))
+        if rc != GICPB_OK:
+            raise GicpError(rc, "gicpb_create failed (no usable sm_100 GPU?); there is no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gicpb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != GICPB_OK:
+            raise GicpError(rc, (self.lib.gicpb_last_error(self.h) or b"").decode())
+
+    # ---- parameters ---------------------------------------------------------------------------------
+    def get_params(self):
+        p = Params()
+        self._check(self.lib.gicpb_get_params(self.h, ctypes.byref(p)))
+        return p
+
+    def set_params(self, **kw):
+        p = self.get_params()
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        self._check(self.lib.gicpb_set_params(self.h, ctypes.byref(p)))
+        return p
+
+    # ---- multi-GPU ----------------------------------------------------------------------------------
+    def nccl_unique_id(self, libnccl=None):
+        buf = (ctypes.c_uint8 * 128)()
+        path = (libnccl or find_libnccl() or "").encode() or None
+        rc = self.lib.gicpb_nccl_unique_id(path, buf)
+        if rc != GICPB_OK:
+            raise GicpError(rc, "gicpb_nccl_unique_id failed")
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id, libnccl=None):
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        path = (libnccl or find_libnccl() or "").encode() or None
+        self._check(self.lib.gicpb_comm_init(self.h, path, rank, world, buf))
+
+    # ---- clouds ---------------------------------------------------------------------------------------
+    def set_target(self, cloud):
+        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        self._check(self.lib.gicpb_set_target(self.h, ptr, n, stride, dev))
+
+    def set_source(self, cloud):
+        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        self._check(self.lib.gicpb_set_source(self.h, ptr, n, stride, dev))
+
+    def compute_covariances(self):
+        self._check(self.lib.gicpb_compute_covariances(self.h))
+
+    def align(self, raise_on_failure=True):
+        res = AlignResult()
+        rc = self.lib.gicpb_align(self.h, ctypes.byref(res))
+        if rc != GICPB_OK and (raise_on_failure or rc in (E_BADARG, E_CUDA, E_NCCL, E_STATE)):
+            self._check(rc)
+        out = {k: getattr(res, k) for k, _ in AlignResult._fields_ if k != "transform"}
+        out["transform"] = np.array(res.transform, np.float32).reshape(4, 4)
+        out["rc"] = rc
+        return out
+
+    def fitness(self, T, max_range=float(np.finfo(np.float64).max)):
+        Tk, Tp = _T(T)
+        s = ctypes.c_double()
+        self._check(self.lib.gicpb_fitness(self.h, Tp, max_range, ctypes.byref(s)))
+        return s.value
+
+    def transform_cloud(self, T, cloud, out=None):
+        Tk, Tp = _T(T)
+        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        if out is None:
+            out = keep.clone() if dev else keep.copy()
+        okeep, optr, on, ostride, odev = _as_cloud(out)
+        if (on, ostride, odev) != (n, stride, dev):
+            raise ValueError("out must match the input cloud's shape, stride and device")
+        self._check(self.lib.gicpb_transform_cloud(self.h, Tp, ptr, optr, n, stride, dev))
+        return okeep
+
+    def cloud_difference(self, input_cloud, subtract_cloud, sqr_threshold):
+        """mask (uint8 numpy, or uint8 CUDA tensor when the clouds are CUDA tensors) and kept count."""
+        ik, iptr, n, istride, idev = _as_cloud(input_cloud)
+        sk, sptr, ns, sstride, sdev = _as_cloud(subtract_cloud)
+        if idev != sdev:
+            raise ValueError("both clouds must live on the same side (host or device)")
+        kept = ctypes.c_int64()
+        if idev:
+            import torch
+            mask = torch.empty(n, dtype=torch.uint8, device=input_cloud.device)
+            mptr = mask.data_ptr()
+        else:
+            mask = np.empty(n, np.uint8)
+            mptr = mask.ctypes.data
+        self._check(self.lib.gicpb_cloud_difference(self.h, iptr, n, istride, sptr, ns, sstride, idev,
+                                                    float(sqr_threshold), mptr, ctypes.byref(kept)))
+        return mask, int(kept.value)
+
+    def difference_set_subtract(self, subtract_cloud):
+        sk, sptr, ns, sstride, sdev = _as_cloud(subtract_cloud)
+        self._check(self.lib.gicpb_difference_set_subtract(self.h, sptr, ns, sstride, sdev))
+
+    def difference_run(self, input_cloud, sqr_threshold, mask=None):
+        ik, iptr, n, istride, idev = _as_cloud(input_cloud)
+        kept = ctypes.c_int64()
+        if mask is None:
+            if idev:
+                import torch
+                mask = torch.empty(n, dtype=torch.uint8, device=input_cloud.device)
+            else:
+                mask = np.empty(n, np.uint8)
+        mdev = 1 if hasattr(mask, "is_cuda") and mask.is_cuda else 0
+        mptr = mask.data_ptr() if hasattr(mask, "data_ptr") else mask.ctypes.data
+        self._check(self.lib.gicpb_difference_run(self.h, iptr, n, istride, idev, float(sqr_threshold), mptr, mdev,
+                                                  ctypes.byref(kept)))
+        return mask, int(kept.value)
+
+    # ---- hooks ----------------------------------------------------------------------------------------
+    def nn1(self, queries, T=None, max_dist=0.0):
+        keep, ptr, n, stride, dev = _as_cloud(queries)
+        idx = np.empty(n, np.int32)
+        d2 = np.empty(n, np.float32)
+        Tp = None
+        if T is not None:
+            Tk, Tp = _T(T)
+        self._check(self.lib.gicpb_nn1(self.h, ptr, n, stride, dev, Tp, float(max_dist),
+                                       idx.ctypes.data_as(c_int32_p), d2.ctypes.data_as(c_float_p)))
+        return idx, d2
+
+    def knn(self, which):
+        info = self.grid_info(which)
+        k = self.get_params().k_correspondences
+        idx = np.empty((info["n_points"], k), np.int32)
+        d2 = np.empty((info["n_points"], k), np.float32)
+        self._check(self.lib.gicpb_knn(self.h, which, idx.ctypes.data_as(c_int32_p), d2.ctypes.data_as(c_float_p)))
+        return idx, d2
+
+    def covariances(self, which):
+        info = self.grid_info(which)
+        cov = np.empty((info["n_points"], 3, 3), np.float64)
+        self._check(self.lib.gicpb_get_covariances(self.h, which, cov.ctypes.data_as(c_double_p)))
+        return cov
+
+    def correspondences(self, T):
+        Tk, Tp = _T(T)
+        n = self.grid_info(1)["n_points"]
+        idx = np.empty(n, np.int32)
+        d2 = np.full(n, np.inf, np.float32)
+        maha = np.empty((n, 3, 3), np.float64)
+        maha[:] = np.eye(3)
+        pairs = ctypes.c_int64()
+        self._check(self.lib.gicpb_correspondences(self.h, Tp, idx.ctypes.data_as(c_int32_p),
+                                                   d2.ctypes.data_as(c_float_p), maha.ctypes.data_as(c_double_p),
+                                                   ctypes.byref(pairs)))
+        return int(pairs.value), idx, d2, maha
+
+    def cost(self, x6):
+        x = np.ascontiguousarray(x6, np.float64)
+        f = ctypes.c_double()
+        g = np.empty(6, np.float64)
+        self._check(self.lib.gicpb_cost(self.h, x.ctypes.data_as(c_double_p), ctypes.byref(f),
+                                        g.ctypes.data_as(c_double_p)))
+        return f.value, g
+
+    def grid_info(self, which):
+        gi = GridInfo()
+        self._check(self.lib.gicpb_grid_info_get(self.h, which, ctypes.byref(gi)))
+        out = {k: getattr(gi, k) for k, _ in GridInfo._fields_ if k != "dims"}
+        out["dims"] = tuple(gi.dims)
+        return out
+
+    def bench_kernel(self, which, T, iters=10):
+        Tk, Tp = _T(T)
+        ms = ctypes.c_double()
+        launches = ctypes.c_int64()
+        self._check(self.lib.gicpb_bench_kernel(self.h, which, Tp, iters, ctypes.byref(ms), ctypes.byref(launches)))
+        return ms.value, int(launches.value)
+
+    def launch_count(self):
+        return int(self.lib.gicpb_launch_count(self.h))

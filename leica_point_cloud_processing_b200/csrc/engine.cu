@@ -1,0 +1,902 @@
+// engine.cu - context object, GICP outer loop and the C ABI of libgicp_b200 (include/gicp_b200.h).
+//
+// Host control flow restates pcl::GeneralizedIterativeClosestPoint::computeTransformation (PCL 1.8.1 gicp.hpp) as
+// the reference drives it from GICPAlignment::fineAlignment / iterateFineAlignment (reference
+// src/GICPAlignment.cpp:86-127): guess = identity, per outer iteration one correspondence pass (kernel) and one
+// BFGS solve (host, optimizer.hpp) whose every evaluation is one cost-kernel launch (+ one NCCL all-reduce of 14
+// doubles when the source is sharded over ranks).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "../../include/gicp_b200.h"
+#include "kernels.hpp"
+#include "optimizer.hpp"
+
+using namespace gicpb;
+
+// ---- NCCL through dlopen -----------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  struct unique_id { char internal[128]; };
+  int (*GetUniqueId)(unique_id*) = nullptr;
+  int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void* handle = nullptr;
+};
+
+NcclApi* load_nccl(const char* path, std::string& err) {
+  static NcclApi api;
+  if (api.handle) return &api;
+  const char* name = (path && *path) ? path : "libnccl.so.2";
+  void* h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    err = std::string("dlopen(") + name + ") failed: " + dlerror();
+    return nullptr;
+  }
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+    err = "libnccl is missing a required symbol";
+    return nullptr;
+  }
+  api.handle = h;
+  return &api;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+struct NcclError : std::runtime_error {
+  explicit NcclError(const std::string& s) : std::runtime_error(s) {}
+};
+struct AlignStop : std::runtime_error {
+  int code;
+  AlignStop(int c, const std::string& s) : std::runtime_error(s), code(c) {}
+};
+
+Rigid rigid_from_rowmajor(const float* T16) {
+  Rigid r;
+  for (int i = 0; i < 12; ++i) r.m[i] = T16[i];
+  return r;
+}
+void identity16(float* T) {
+  for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
+}
+
+// gicp.hpp applyState: R = Rz(x5) Ry(x4) Rx(x3) built in float through quaternions (Eigen AngleAxisf products),
+// t.topLeft3x3 = R * t.topLeft3x3, t.col(3) += (x0,x1,x2).  Here t starts as the identity (base_transformation_).
+struct Quat {
+  float w, x, y, z;
+};
+Quat quat_axis(float angle, int axis) {
+  const float ha = 0.5f * angle;
+  Quat q{std::cos(ha), 0.f, 0.f, 0.f};
+  const float s = std::sin(ha);
+  (axis == 0 ? q.x : axis == 1 ? q.y : q.z) = s;
+  return q;
+}
+Quat quat_mul(const Quat& a, const Quat& b) {
+  return Quat{a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+              a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+void state_to_transform(const double* x, float* T16) {
+  const Quat q = quat_mul(quat_mul(quat_axis((float)x[5], 2), quat_axis((float)x[4], 1)), quat_axis((float)x[3], 0));
+  const float tx = 2.f * q.x, ty = 2.f * q.y, tz = 2.f * q.z;
+  const float twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const float txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const float tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  const float R[9] = {1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
+                      txz - twy, tyz + twx, 1.f - (txx + tyy)};
+  identity16(T16);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      // R * I evaluated as Eigen's lazy product does: (r_i0*I_0j + r_i1*I_1j) + r_i2*I_2j
+      float s = R[3 * i] * (j == 0 ? 1.f : 0.f);
+      s = s + R[3 * i + 1] * (j == 1 ? 1.f : 0.f);
+      s = s + R[3 * i + 2] * (j == 2 ? 1.f : 0.f);
+      T16[4 * i + j] = s;
+    }
+  T16[3] += (float)x[0];
+  T16[7] += (float)x[1];
+  T16[11] += (float)x[2];
+}
+void transform_to_state(const float* T, double* x) {
+  x[0] = T[3];
+  x[1] = T[7];
+  x[2] = T[11];
+  x[3] = std::atan2((double)T[9], (double)T[10]);
+  x[4] = std::asin(-(double)T[8]);
+  x[5] = std::atan2((double)T[4], (double)T[0]);
+}
+
+// gicp.hpp computeRDerivative: g[3..5] = sum_ij dR(j,i) * Rsum(i,j)
+void rotation_gradient(const double* x, const double* Rs, double* g) {
+  const double cphi = std::cos(x[3]), sphi = std::sin(x[3]);
+  const double cth = std::cos(x[4]), sth = std::sin(x[4]);
+  const double cpsi = std::cos(x[5]), spsi = std::sin(x[5]);
+  double dphi[9] = {0, sphi * spsi + cphi * cpsi * sth, cphi * spsi - cpsi * sphi * sth,
+                    0, -cpsi * sphi + cphi * spsi * sth, -cphi * cpsi - sphi * spsi * sth,
+                    0, cphi * cth, -cth * sphi};
+  double dth[9] = {-cpsi * sth, cpsi * cth * sphi, cphi * cpsi * cth,
+                   -spsi * sth, cth * sphi * spsi, cphi * cth * spsi,
+                   -cth, -sphi * sth, -cphi * sth};
+  double dpsi[9] = {-cth * spsi, -cphi * cpsi - sphi * spsi * sth, cpsi * sphi - cphi * spsi * sth,
+                    cpsi * cth, -cphi * spsi + cpsi * sphi * sth, sphi * spsi + cphi * cpsi * sth,
+                    0, 0, 0};
+  auto inner = [&](const double* d) {
+    double r = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r += d[3 * j + i] * Rs[3 * i + j];
+    return r;
+  };
+  g[3] = inner(dphi);
+  g[4] = inner(dth);
+  g[5] = inner(dpsi);
+}
+
+float round_up_to_float(double v) {  // smallest float >= v
+  float f = (float)v;
+  if ((double)f < v) f = std::nextafterf(f, INFINITY);
+  return f;
+}
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ---- context ------------------------------------------------------------------------------------------------
+struct gicpb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  gicpb_params prm{};
+  std::string err;
+
+  GridIndex tgt, src, sub;
+  bool cov_ready = false;
+  int shard_lo = 0, shard_hi = 0;
+  DevBuf<double> n_tgt, n_src;
+  DevBuf<int> pair_pos;
+  DevBuf<float> pair_d2;
+  DevBuf<float4> pair_tgt;
+  DevBuf<double> maha;  // 6 doubles (or 6 floats) per shard point
+  bool pairs_valid = false;
+  bool pairs_fp32 = false;
+  DevBuf<double> partials;
+  DevBuf<unsigned> ticket;
+  DevBuf<double> d_sums;          // 16 doubles on the device (NCCL path / fitness)
+  double* h_sums = nullptr;       // pinned, mapped
+  double* h_sums_dev = nullptr;   // device alias of h_sums
+  DevBuf<float4> queries;
+  DevBuf<unsigned char> io_a, io_b;
+  DevBuf<unsigned long long> counter;
+
+  NcclApi* nccl = nullptr;
+  NcclApi::comm_t comm = nullptr;
+  int rank = 0, world = 1;
+
+  // accounting
+  double ms_corr = 0, ms_cost = 0;
+  int64_t cost_evals = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+template <typename F>
+int guarded(gicpb_ctx* ctx, F&& fn) {
+  if (!ctx) return GICPB_E_BADARG;
+  DeviceGuard guard(ctx->device);
+  try {
+    fn();
+    return GICPB_OK;
+  } catch (const ArgError& e) {
+    ctx->err = e.what();
+    return GICPB_E_BADARG;
+  } catch (const StateError& e) {
+    ctx->err = e.what();
+    return GICPB_E_STATE;
+  } catch (const CudaError& e) {
+    ctx->err = e.what();
+    return GICPB_E_CUDA;
+  } catch (const NcclError& e) {
+    ctx->err = e.what();
+    return GICPB_E_NCCL;
+  } catch (const AlignStop& e) {
+    ctx->err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+    return GICPB_E_CUDA;
+  }
+}
+
+void check_nccl(gicpb_ctx* c, int rc, const char* what) {
+  if (rc != 0) throw NcclError(std::string(what) + ": " + c->nccl->GetErrorString(rc));
+}
+
+void all_reduce_sum(gicpb_ctx* c, double* dev, int count) {
+  if (c->world <= 1) return;
+  check_nccl(c, c->nccl->AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream), "ncclAllReduce");
+}
+
+void update_shard(gicpb_ctx* c) {
+  const int64_t n = c->src.ready() ? c->src.n_indexed() : 0;
+  c->shard_lo = (int)(n * c->rank / c->world);
+  c->shard_hi = (int)(n * (c->rank + 1) / c->world);
+}
+
+void ensure_covariances(gicpb_ctx* c) {
+  if (c->cov_ready) return;
+  if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
+  const int k = c->prm.k_correspondences;
+  if (k < 2 || k > 32) throw ArgError("k_correspondences must be in [2, 32]");
+  if (k > c->tgt.n_indexed() || k > c->src.n_indexed())
+    throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points in a cloud");
+  update_shard(c);
+  const int ns = c->shard_hi - c->shard_lo;
+  c->n_tgt.reserve(3 * (size_t)c->tgt.n_indexed());
+  c->n_src.reserve(3 * (size_t)std::max(ns, 1));
+  launch_knn_covariances(c->tgt.view(), 0, c->tgt.n_indexed(), k, c->n_tgt.get(), nullptr, nullptr, c->stream);
+  launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, c->stream);
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  c->cov_ready = true;
+  c->pairs_valid = false;
+}
+
+void ensure_pair_buffers(gicpb_ctx* c) {
+  const size_t ns = (size_t)std::max(c->shard_hi - c->shard_lo, 1);
+  c->pair_pos.reserve(ns);
+  c->pair_d2.reserve(ns);
+  c->pair_tgt.reserve(ns);
+  c->maha.reserve(6 * ns);
+  c->partials.reserve((size_t)c->num_sms * 4 * kCostSums + 2 * (size_t)fitness_partial_rows((int)ns) + 64);
+  c->ticket.reserve(4);
+  c->d_sums.reserve(16);
+}
+
+// one correspondence pass under transform T (row-major 4x4 float)
+void run_correspondences(gicpb_ctx* c, const float* T16, bool first) {
+  ensure_pair_buffers(c);
+  const Rigid T = rigid_from_rowmajor(T16);
+  RotD R;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R.m[3 * i + j] = (double)T16[4 * i + j];
+  const double thr = c->prm.max_corr_distance * c->prm.max_corr_distance;
+  const float gate2 = round_up_to_float(thr);
+  const bool fp32 = c->prm.mahalanobis_fp32 != 0;
+  const bool use_prev = c->prm.use_previous_match != 0 && !first && c->pairs_valid && c->pairs_fp32 == fp32;
+  GICPB_CUDA(cudaEventRecord(c->ev0, c->stream));
+  launch_correspondences(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, R, gate2, c->n_src.get(),
+                         c->n_tgt.get(), c->prm.gicp_epsilon, c->pair_pos.get(), c->pair_d2.get(), c->pair_tgt.get(),
+                         c->maha.get(), fp32, use_prev, c->stream);
+  GICPB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  c->pairs_valid = true;
+  c->pairs_fp32 = fp32;
+}
+
+// raw sums of one evaluation at x (all ranks): s[0] = sum r.Mr, s[1..3] = sum Mr, s[4..12] = sum p (Mr)^T, s[13] = m
+void run_cost(gicpb_ctx* c, const double* x, double* sums) {
+  float T16[16];
+  state_to_transform(x, T16);
+  const Rigid T = rigid_from_rowmajor(T16);
+  const int n = c->shard_hi - c->shard_lo;
+  const int blocks = cost_grid_blocks(n, c->num_sms);
+  double* out = (c->world > 1) ? c->d_sums.get() : c->h_sums_dev;
+  launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32, T,
+              c->partials.get(), c->ticket.get(), out, blocks, c->stream);
+  if (c->world > 1) {
+    all_reduce_sum(c, c->d_sums.get(), kCostSums);
+    GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), kCostSums * sizeof(double), cudaMemcpyDeviceToHost,
+                               c->stream));
+  }
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < kCostSums; ++i) sums[i] = c->h_sums[i];
+  ++c->cost_evals;
+}
+
+// f and g[6] exactly as OptimizationFunctorWithIndices::fdf scales them; returns the pair count
+double cost_from_sums(const double* x, const double* s, double* f, double* g) {
+  const double m = s[13];
+  *f = s[0] / m;
+  const double sc = 2.0 / m;
+  g[0] = s[1] * sc;
+  g[1] = s[2] * sc;
+  g[2] = s[3] * sc;
+  double Rs[9];
+  for (int i = 0; i < 9; ++i) Rs[i] = s[4 + i] * sc;
+  rotation_gradient(x, Rs, g);
+  return m;
+}
+
+void do_align(gicpb_ctx* c, gicpb_align_result* out) {
+  const double t_begin = now_ms();
+  std::memset(out, 0, sizeof(*out));
+  identity16(out->transform);
+  if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
+  ensure_covariances(c);
+  ensure_pair_buffers(c);
+  c->ms_corr = c->ms_cost = 0;
+  c->cost_evals = 0;
+
+  float T[16], prev[16];
+  identity16(T);
+  identity16(prev);
+  int nr_iterations = 0, inner_total = 0;
+  bool converged = false;
+  int status = GICPB_OK;
+  int64_t corr_queries = 0;
+  double pairs_last = 0;
+  const int max_iterations = c->prm.max_iterations;
+
+  while (!converged) {
+    run_correspondences(c, T, nr_iterations == 0);
+    corr_queries += c->src.n_indexed();
+    std::memcpy(prev, T, sizeof(T));
+
+    double x[6];
+    transform_to_state(T, x);
+    double m_pairs = 0;
+    bool first_eval = true;
+    Bfgs6 bfgs([&](const double* xx, double* f, double* g) {
+      double s[kCostSums];
+      const double t0 = now_ms();
+      run_cost(c, xx, s);
+      c->ms_cost += now_ms() - t0;
+      if (first_eval) {
+        first_eval = false;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->ms_corr += ms;
+      }
+      m_pairs = s[13];
+      if (m_pairs < 4.0) return false;  // NotEnoughPointsException (< 4 correspondences)
+      cost_from_sums(xx, s, f, g);
+      return true;
+    });
+    if (!bfgs.init(x)) {
+      pairs_last = m_pairs;
+      status = GICPB_E_NOT_ENOUGH_CORRESPONDENCES;
+      break;
+    }
+    pairs_last = m_pairs;
+    int inner = 0;
+    BfgsStatus result = BfgsStatus::kRunning;
+    do {
+      ++inner;
+      result = bfgs.step(x);
+      if (result != BfgsStatus::kSuccess) break;
+      result = (bfgs.gradient_norm() < 1e-2) ? BfgsStatus::kSuccess : BfgsStatus::kRunning;
+    } while (result == BfgsStatus::kRunning && inner < c->prm.max_inner_iterations);
+    inner_total += inner;
+    if (result == BfgsStatus::kNoProgress || result == BfgsStatus::kSuccess || inner == c->prm.max_inner_iterations) {
+      state_to_transform(x, T);
+    } else {
+      status = GICPB_E_SOLVER;
+      break;
+    }
+    double delta = 0.0;
+    for (int k = 0; k < 4; ++k)
+      for (int l = 0; l < 4; ++l) {
+        const double ratio = (k < 3 && l < 3) ? 1.0 / c->prm.rotation_epsilon : 1.0 / c->prm.transformation_epsilon;
+        const double cd = ratio * std::fabs((double)(prev[4 * k + l] - T[4 * k + l]));
+        if (cd > delta) delta = cd;
+      }
+    ++nr_iterations;
+    if (nr_iterations >= max_iterations || delta < 1) {
+      converged = true;
+      std::memcpy(prev, T, sizeof(T));
+    }
+  }
+  std::memcpy(out->transform, prev, sizeof(prev));  // final_transformation_ = previous_transformation_ * guess
+  out->converged = converged ? 1 : 0;
+  out->status = status;
+  out->outer_iterations = nr_iterations;
+  out->inner_iterations = inner_total;
+  out->cost_evaluations = c->cost_evals;
+  out->corr_queries = corr_queries;
+  out->corr_pairs_last = (int64_t)pairs_last;
+  out->ms_corr = c->ms_corr;
+  out->ms_cost = c->ms_cost;
+  out->ms_total = now_ms() - t_begin;
+  if (status == GICPB_E_NOT_ENOUGH_CORRESPONDENCES) c->err = "fewer than 4 correspondences inside the distance gate";
+  if (status == GICPB_E_SOLVER) c->err = "BFGS did not converge";
+}
+
+const unsigned char* stage_in(gicpb_ctx* c, DevBuf<unsigned char>& buf, const void* p, int64_t n, int64_t stride,
+                              bool on_device) {
+  if (on_device) return static_cast<const unsigned char*>(p);
+  const size_t bytes = (size_t)(n - 1) * stride + 12;
+  buf.reserve((size_t)n * stride);
+  GICPB_CUDA(cudaMemcpyAsync(buf.get(), p, bytes, cudaMemcpyHostToDevice, c->stream));
+  return buf.get();
+}
+
+void check_cloud_args(const void* p, int64_t n, int64_t stride) {
+  if (!p) throw ArgError("null cloud pointer");
+  if (n <= 0) throw ArgError("cloud is empty");
+  if (stride < 12 || stride % 4) throw ArgError("stride must be a multiple of 4 and >= 12");
+  if (reinterpret_cast<uintptr_t>(p) % 4) throw ArgError("cloud pointer must be 4-byte aligned");
+}
+
+GridIndex& pick_grid(gicpb_ctx* c, int which) {
+  if (which == 0) return c->tgt;
+  if (which == 1) return c->src;
+  if (which == 2) return c->sub;
+  throw ArgError("which must be 0 (target), 1 (source) or 2 (subtract)");
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+void gicpb_default_params(gicpb_params* p) {
+  if (!p) return;
+  p->max_iterations = 100;
+  p->transformation_epsilon = 4e-3;
+  p->rotation_epsilon = 2e-3;
+  p->max_corr_distance = 4e-2;
+  p->k_correspondences = 20;
+  p->gicp_epsilon = 1e-3;
+  p->max_inner_iterations = 20;
+  p->cell_size = 0.f;
+  p->points_per_cell = 3.0f;
+  p->mahalanobis_fp32 = 0;
+  p->use_previous_match = 1;
+}
+
+int gicpb_create(int device, gicpb_ctx** out) {
+  if (!out) return GICPB_E_BADARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return GICPB_E_CUDA;
+  std::unique_ptr<gicpb_ctx> c(new gicpb_ctx);
+  c->device = device;
+  gicpb_default_params(&c->prm);
+  DeviceGuard guard(device);
+  try {
+    cudaDeviceProp prop;
+    GICPB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw CudaError("libgicp_b200 is built for sm_100a only; found sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor));
+    c->num_sms = prop.multiProcessorCount;
+    GICPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GICPB_CUDA(cudaEventCreate(&c->ev0));
+    GICPB_CUDA(cudaEventCreate(&c->ev1));
+    GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
+    GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
+    c->ticket.reserve(4);
+    GICPB_CUDA(cudaMemset(c->ticket.get(), 0, 4 * sizeof(unsigned)));
+    c->counter.reserve(2);
+  } catch (const std::exception&) {
+    return GICPB_E_CUDA;
+  }
+  *out = c.release();
+  return GICPB_OK;
+}
+
+void gicpb_destroy(gicpb_ctx* c) {
+  if (!c) return;
+  DeviceGuard guard(c->device);
+  if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->h_sums) cudaFreeHost(c->h_sums);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* gicpb_last_error(const gicpb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int gicpb_set_params(gicpb_ctx* c, const gicpb_params* p) {
+  return guarded(c, [&] {
+    if (!p) throw ArgError("null params");
+    if (p->k_correspondences < 2 || p->k_correspondences > 32) throw ArgError("k_correspondences must be in [2, 32]");
+    if (p->max_iterations < 1) throw ArgError("max_iterations must be >= 1");
+    if (!(p->gicp_epsilon > 0)) throw ArgError("gicp_epsilon must be > 0");
+    const bool cov_changed = p->k_correspondences != c->prm.k_correspondences;
+    c->prm = *p;
+    if (cov_changed) c->cov_ready = false;
+  });
+}
+
+int gicpb_get_params(const gicpb_ctx* c, gicpb_params* p) {
+  if (!c || !p) return GICPB_E_BADARG;
+  *p = c->prm;
+  return GICPB_OK;
+}
+
+int gicpb_nccl_unique_id(const char* libnccl_path, unsigned char id_out[128]) {
+  std::string err;
+  NcclApi* api = load_nccl(libnccl_path, err);
+  if (!api || !id_out) return GICPB_E_NCCL;
+  NcclApi::unique_id id;
+  if (api->GetUniqueId(&id) != 0) return GICPB_E_NCCL;
+  std::memcpy(id_out, id.internal, 128);
+  return GICPB_OK;
+}
+
+int gicpb_comm_init(gicpb_ctx* c, const char* libnccl_path, int rank, int world, const unsigned char id[128]) {
+  return guarded(c, [&] {
+    if (world < 1 || rank < 0 || rank >= world) throw ArgError("bad rank / world");
+    if (world == 1) {
+      c->rank = 0;
+      c->world = 1;
+      return;
+    }
+    if (!id) throw ArgError("null NCCL unique id");
+    std::string err;
+    c->nccl = load_nccl(libnccl_path, err);
+    if (!c->nccl) throw NcclError(err);
+    NcclApi::unique_id uid;
+    std::memcpy(uid.internal, id, 128);
+    check_nccl(c, c->nccl->CommInitRank(&c->comm, world, uid, rank), "ncclCommInitRank");
+    c->rank = rank;
+    c->world = world;
+    c->cov_ready = false;
+    c->pairs_valid = false;
+    update_shard(c);
+  });
+}
+
+int gicpb_comm_rank(const gicpb_ctx* c, int* rank, int* world) {
+  if (!c) return GICPB_E_BADARG;
+  if (rank) *rank = c->rank;
+  if (world) *world = c->world;
+  return GICPB_OK;
+}
+
+int gicpb_set_target(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, int on_device) {
+  return guarded(c, [&] {
+    check_cloud_args(xyz, n, stride);
+    c->cov_ready = false;
+    c->pairs_valid = false;
+    c->tgt.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+  });
+}
+
+int gicpb_set_source(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, int on_device) {
+  return guarded(c, [&] {
+    check_cloud_args(xyz, n, stride);
+    c->cov_ready = false;
+    c->pairs_valid = false;
+    c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    update_shard(c);
+  });
+}
+
+int gicpb_compute_covariances(gicpb_ctx* c) {
+  return guarded(c, [&] { ensure_covariances(c); });
+}
+
+int gicpb_align(gicpb_ctx* c, gicpb_align_result* out) {
+  if (!out) return GICPB_E_BADARG;
+  int rc = guarded(c, [&] { do_align(c, out); });
+  if (rc == GICPB_OK && out->status != GICPB_OK) rc = out->status;
+  return rc;
+}
+
+int gicpb_fitness(gicpb_ctx* c, const float transform[16], double max_range, double* score) {
+  return guarded(c, [&] {
+    if (!transform || !score) throw ArgError("null argument");
+    if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
+    update_shard(c);
+    ensure_pair_buffers(c);
+    const Rigid T = rigid_from_rowmajor(transform);
+    double* partials = c->partials.get() + (size_t)c->num_sms * 4 * kCostSums;
+    launch_fitness(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, max_range, partials,
+                   c->d_sums.get(), c->stream);
+    all_reduce_sum(c, c->d_sums.get(), 2);
+    GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    *score = c->h_sums[1] > 0 ? c->h_sums[0] / c->h_sums[1] : std::numeric_limits<double>::max();
+  });
+}
+
+int gicpb_transform_cloud(gicpb_ctx* c, const float transform[16], const void* in, void* out, int64_t n, int64_t stride,
+                          int on_device) {
+  return guarded(c, [&] {
+    if (!transform || !out) throw ArgError("null argument");
+    check_cloud_args(in, n, stride);
+    const Rigid T = rigid_from_rowmajor(transform);
+    if (on_device) {
+      launch_transform(static_cast<const unsigned char*>(in), static_cast<unsigned char*>(out), n, stride, T, c->stream);
+      GICPB_CUDA(cudaStreamSynchronize(c->stream));
+      return;
+    }
+    // host clouds: `in` / `out` point at the first x; the last point may end right after its z
+    const size_t bytes = (size_t)(n - 1) * stride + 12;
+    const size_t full = (size_t)n * stride;
+    c->io_a.reserve(full);
+    GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), in, bytes, cudaMemcpyHostToDevice, c->stream));
+    launch_transform(c->io_a.get(), c->io_a.get(), n, stride, T, c->stream);
+    GICPB_CUDA(cudaMemcpyAsync(out, c->io_a.get(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int gicpb_difference_set_subtract(gicpb_ctx* c, const void* subtract, int64_t n, int64_t stride, int on_device) {
+  return guarded(c, [&] {
+    check_cloud_args(subtract, n, stride);
+    c->sub.build(subtract, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+  });
+}
+
+int gicpb_difference_run(gicpb_ctx* c, const void* input, int64_t n, int64_t stride, int on_device, double thr,
+                         uint8_t* mask, int mask_on_device, int64_t* n_kept) {
+  return guarded(c, [&] {
+    if (!mask) throw ArgError("null mask");
+    check_cloud_args(input, n, stride);
+    if (!c->sub.ready()) throw StateError("difference_set_subtract must be called first");
+    const unsigned char* d_in = stage_in(c, c->io_a, input, n, stride, on_device != 0);
+    unsigned char* d_mask = mask;
+    if (!mask_on_device) {
+      c->io_b.reserve((size_t)n);
+      d_mask = c->io_b.get();
+    }
+    GICPB_CUDA(cudaMemsetAsync(c->counter.get(), 0, sizeof(unsigned long long), c->stream));
+    // keep iff (double)d2 > thr.  With thr_f = largest float <= thr this is d2 > thr_f, i.e. NOT (d2 < next(thr_f)).
+    bool always_keep = thr < 0;
+    float thr_next = 0.f;
+    if (!always_keep) {
+      float tf = (float)thr;
+      if ((double)tf > thr) tf = std::nextafterf(tf, -INFINITY);
+      thr_next = std::nextafterf(tf, INFINITY);
+    }
+    launch_difference(c->sub.view(), d_in, n, stride, thr_next, always_keep, d_mask, c->counter.get(), c->stream);
+    unsigned long long kept = 0;
+    GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
+    if (!mask_on_device) GICPB_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_kept) *n_kept = (int64_t)kept;
+  });
+}
+
+int gicpb_cloud_difference(gicpb_ctx* c, const void* input, int64_t n_input, int64_t input_stride, const void* subtract,
+                           int64_t n_subtract, int64_t subtract_stride, int on_device, double thr, uint8_t* mask,
+                           int64_t* n_kept) {
+  int rc = gicpb_difference_set_subtract(c, subtract, n_subtract, subtract_stride, on_device);
+  if (rc != GICPB_OK) return rc;
+  return gicpb_difference_run(c, input, n_input, input_stride, on_device, thr, mask, on_device, n_kept);
+}
+
+int gicpb_nn1(gicpb_ctx* c, const void* queries, int64_t n, int64_t stride, int on_device, const float transform[16],
+              double max_dist, int32_t* idx, float* d2) {
+  return guarded(c, [&] {
+    check_cloud_args(queries, n, stride);
+    if (!c->tgt.ready()) throw StateError("set_target must be called first");
+    if (n > INT_MAX) throw ArgError("too many queries");
+    float ident[16];
+    identity16(ident);
+    const Rigid T = rigid_from_rowmajor(transform ? transform : ident);
+    const unsigned char* d_in = stage_in(c, c->io_a, queries, n, stride, on_device != 0);
+    c->queries.reserve((size_t)n);
+    launch_pack_queries(d_in, n, stride, c->queries.get(), c->stream);
+    c->io_b.reserve((size_t)n * 8);
+    int* d_idx = reinterpret_cast<int*>(c->io_b.get());
+    float* d_d2 = reinterpret_cast<float*>(c->io_b.get() + (size_t)n * 4);
+    const float gate2 = max_dist > 0 ? round_up_to_float(max_dist * max_dist) : 0.f;
+    launch_nn1(c->tgt.view(), c->queries.get(), (int)n, T, gate2, d_idx, d_d2, nullptr, c->stream);
+    if (idx) GICPB_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d2) GICPB_CUDA(cudaMemcpyAsync(d2, d_d2, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int gicpb_knn(gicpb_ctx* c, int which, int32_t* idx, float* d2) {
+  return guarded(c, [&] {
+    if (!idx || !d2) throw ArgError("null output");
+    if (which != 0 && which != 1) throw ArgError("which must be 0 or 1");
+    GridIndex& g = pick_grid(c, which);
+    if (!g.ready()) throw StateError("cloud not set");
+    const int k = c->prm.k_correspondences;
+    const int n = g.n_indexed();
+    if (k > n) throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points");
+    DevBuf<double> normals;
+    DevBuf<int> d_idx;
+    DevBuf<float> d_d2;
+    normals.reserve(3 * (size_t)n);
+    d_idx.reserve((size_t)n * k);
+    d_d2.reserve((size_t)n * k);
+    launch_knn_covariances(g.view(), 0, n, k, normals.get(), d_idx.get(), d_d2.get(), c->stream);
+    std::vector<int> hi((size_t)n * k);
+    std::vector<float> hd((size_t)n * k);
+    std::vector<float4> hp((size_t)n);
+    GICPB_CUDA(cudaMemcpyAsync(hi.data(), d_idx.get(), hi.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(hd.data(), d_d2.get(), hd.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(hp.data(), g.sorted_points(), hp.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t total = g.n_points();
+    for (int64_t i = 0; i < total * k; ++i) {
+      idx[i] = -1;
+      d2[i] = INFINITY;
+    }
+    for (int s = 0; s < n; ++s) {
+      int oi;
+      std::memcpy(&oi, &hp[s].w, 4);
+      std::memcpy(idx + (size_t)oi * k, hi.data() + (size_t)s * k, (size_t)k * 4);
+      std::memcpy(d2 + (size_t)oi * k, hd.data() + (size_t)s * k, (size_t)k * 4);
+    }
+  });
+}
+
+int gicpb_get_covariances(gicpb_ctx* c, int which, double* cov9) {
+  return guarded(c, [&] {
+    if (!cov9) throw ArgError("null output");
+    if (which != 0 && which != 1) throw ArgError("which must be 0 or 1");
+    ensure_covariances(c);
+    GridIndex& g = pick_grid(c, which);
+    const int lo = which == 0 ? 0 : c->shard_lo;
+    const int hi = which == 0 ? g.n_indexed() : c->shard_hi;
+    const int n = hi - lo;
+    std::vector<double> hn(3 * (size_t)std::max(n, 1));
+    std::vector<float4> hp((size_t)g.n_indexed());
+    GICPB_CUDA(cudaMemcpyAsync(hn.data(), (which == 0 ? c->n_tgt : c->n_src).get(), 3 * (size_t)n * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(hp.data(), g.sorted_points(), hp.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    const double a = 1.0 - c->prm.gicp_epsilon;
+    const int64_t total = g.n_points();
+    for (int64_t i = 0; i < 9 * total; ++i) cov9[i] = std::numeric_limits<double>::quiet_NaN();
+    for (int s = 0; s < n; ++s) {
+      int oi;
+      std::memcpy(&oi, &hp[lo + s].w, 4);
+      const double* nn = &hn[3 * (size_t)s];
+      double* C = cov9 + 9 * (size_t)oi;
+      for (int r = 0; r < 3; ++r)
+        for (int q = 0; q < 3; ++q) C[3 * r + q] = (r == q ? 1.0 : 0.0) - a * nn[r] * nn[q];
+    }
+  });
+}
+
+int gicpb_correspondences(gicpb_ctx* c, const float transform[16], int32_t* nn_idx, float* d2, double* maha9,
+                          int64_t* n_pairs) {
+  return guarded(c, [&] {
+    if (!transform) throw ArgError("null transform");
+    ensure_covariances(c);
+    run_correspondences(c, transform, true);
+    const int lo = c->shard_lo, n = c->shard_hi - c->shard_lo;
+    std::vector<int> hpos((size_t)std::max(n, 1));
+    std::vector<float> hd2((size_t)std::max(n, 1));
+    std::vector<float4> hs((size_t)c->src.n_indexed()), ht((size_t)c->tgt.n_indexed());
+    std::vector<double> hm;
+    std::vector<float> hmf;
+    GICPB_CUDA(cudaMemcpyAsync(hpos.data(), c->pair_pos.get(), (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(hd2.data(), c->pair_d2.get(), (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(hs.data(), c->src.sorted_points(), hs.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(ht.data(), c->tgt.sorted_points(), ht.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (c->pairs_fp32) {
+      hmf.resize(6 * (size_t)std::max(n, 1));
+      GICPB_CUDA(cudaMemcpyAsync(hmf.data(), c->maha.get(), 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    } else {
+      hm.resize(6 * (size_t)std::max(n, 1));
+      GICPB_CUDA(cudaMemcpyAsync(hm.data(), c->maha.get(), 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    const int64_t total = c->src.n_points();
+    if (nn_idx) for (int64_t i = 0; i < total; ++i) nn_idx[i] = -2;
+    int64_t pairs = 0;
+    for (int s = 0; s < n; ++s) {
+      int oi;
+      std::memcpy(&oi, &hs[lo + s].w, 4);
+      int tj = -1;
+      if (hpos[s] >= 0) {
+        std::memcpy(&tj, &ht[hpos[s]].w, 4);
+        ++pairs;
+      }
+      if (nn_idx) nn_idx[oi] = tj;
+      if (d2) d2[oi] = hd2[s];
+      if (maha9) {
+        double* M = maha9 + 9 * (size_t)oi;
+        if (tj < 0) {
+          for (int e = 0; e < 9; ++e) M[e] = (e % 4 == 0) ? 1.0 : 0.0;
+        } else {
+          double v[6];
+          for (int e = 0; e < 6; ++e) v[e] = c->pairs_fp32 ? (double)hmf[6 * (size_t)s + e] : hm[6 * (size_t)s + e];
+          M[0] = v[0]; M[1] = v[1]; M[2] = v[2];
+          M[3] = v[1]; M[4] = v[3]; M[5] = v[4];
+          M[6] = v[2]; M[7] = v[4]; M[8] = v[5];
+        }
+      }
+    }
+    if (n_pairs) *n_pairs = pairs;
+  });
+}
+
+int gicpb_cost(gicpb_ctx* c, const double x[6], double* f, double g[6]) {
+  return guarded(c, [&] {
+    if (!x || !f || !g) throw ArgError("null argument");
+    if (!c->pairs_valid) throw StateError("no correspondences: call gicpb_correspondences or gicpb_align first");
+    double s[kCostSums];
+    run_cost(c, x, s);
+    if (s[13] < 1.0) throw AlignStop(GICPB_E_NOT_ENOUGH_CORRESPONDENCES, "no correspondences");
+    cost_from_sums(x, s, f, g);
+  });
+}
+
+int gicpb_grid_info_get(gicpb_ctx* c, int which, gicpb_grid_info* out) {
+  return guarded(c, [&] {
+    if (!out) throw ArgError("null output");
+    GridIndex& g = pick_grid(c, which);
+    if (!g.ready()) throw StateError("cloud not set");
+    const GridIndex::Info& i = g.info();
+    out->n_points = i.n_points;
+    out->n_indexed = i.n_indexed;
+    out->cell_size = i.cell_size;
+    for (int a = 0; a < 3; ++a) out->dims[a] = i.dims[a];
+    out->n_bricks_occupied = i.n_bricks_occupied;
+    out->n_cells_occupied = i.n_cells_occupied;
+    out->ms_build = i.ms_build;
+  });
+}
+
+int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int iters, double* ms_mean, int64_t* launches) {
+  return guarded(c, [&] {
+    if (!transform || !ms_mean || iters < 1) throw ArgError("bad argument");
+    ensure_covariances(c);
+    ensure_pair_buffers(c);
+    const Rigid T = rigid_from_rowmajor(transform);
+    const int n = c->shard_hi - c->shard_lo;
+    double x[6];
+    transform_to_state(transform, x);
+    if (which == 1 && !c->pairs_valid) run_correspondences(c, transform, true);
+    if (which == 2) c->io_b.reserve((size_t)n * 8);
+    const int64_t before = g_launch_count;
+    float total = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      if (which == 0) {
+        run_correspondences(c, transform, true);  // records ev0 / ev1 around the kernel
+      } else if (which == 1) {
+        float T16[16];
+        state_to_transform(x, T16);
+        GICPB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32,
+                    rigid_from_rowmajor(T16), c->partials.get(), c->ticket.get(), c->d_sums.get(),
+                    cost_grid_blocks(n, c->num_sms), c->stream);
+        GICPB_CUDA(cudaEventRecord(c->ev1, c->stream));
+      } else if (which == 2) {
+        const float gate2 = round_up_to_float(c->prm.max_corr_distance * c->prm.max_corr_distance);
+        GICPB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        launch_nn1(c->tgt.view(), c->src.sorted_points() + c->shard_lo, n, T, gate2,
+                   reinterpret_cast<int*>(c->io_b.get()), reinterpret_cast<float*>(c->io_b.get() + (size_t)n * 4), nullptr,
+                   c->stream);
+        GICPB_CUDA(cudaEventRecord(c->ev1, c->stream));
+      } else {
+        throw ArgError("which must be 0, 1 or 2");
+      }
+      GICPB_CUDA(cudaEventSynchronize(c->ev1));
+      float ms = 0.f;
+      GICPB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      total += ms;
+    }
+    *ms_mean = total / iters;
+    if (launches) *launches = g_launch_count - before;
+  });
+}
+
+int64_t gicpb_launch_count(const gicpb_ctx*) { return g_launch_count; }
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// engine.hpp - host-side declarations shared by the translation units of libgicp_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gicpb {
+
+struct CudaError : std::runtime_error {
+  explicit CudaError(const std::string& s) : std::runtime_error(s) {}
+};
+struct ArgError : std::runtime_error {
+  explicit ArgError(const std::string& s) : std::runtime_error(s) {}
+};
+struct StateError : std::runtime_error {
+  explicit StateError(const std::string& s) : std::runtime_error(s) {}
+};
+
+#define GICPB_CUDA(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw ::gicpb::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                               ":" + std::to_string(__LINE__) + ")");                                 \
+  } while (0)
+
+extern int64_t g_launch_count;  // kernels launched by this library (all contexts)
+#define GICPB_LAUNCHED()                 \
+  do {                                   \
+    ++::gicpb::g_launch_count;           \
+    GICPB_CUDA(cudaGetLastError());      \
+  } while (0)
+
+// RAII device buffer (cudaMalloc); never shrinks unless released
+template <typename T>
+class DevBuf {
+ public:
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p_) cudaFree(p_);
+    p_ = nullptr;
+    cap_ = 0;
+  }
+  void reserve(size_t n) {
+    if (n <= cap_) return;
+    release();
+    GICPB_CUDA(cudaMalloc(&p_, std::max<size_t>(n, 1) * sizeof(T)));
+    cap_ = n;
+  }
+  T* get() const { return p_; }
+  size_t capacity() const { return cap_; }
+
+ private:
+  T* p_ = nullptr;
+  size_t cap_ = 0;
+};
+
+// Per-cloud spatial index (see common.cuh).  build() runs the whole pipeline on `stream`:
+// ingest (strided xyz -> float4 + bbox) -> density probe -> cell keys -> radix sort -> reorder -> brick/cell tables.
+class GridIndex {
+ public:
+  struct Info {
+    int64_t n_points = 0, n_indexed = 0;
+    float cell_size = 0;
+    int dims[3] = {0, 0, 0};
+    int64_t n_bricks_occupied = 0, n_cells_occupied = 0;
+    double ms_build = 0;
+    float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+  };
+  // `raw` points at the first x; device pointer iff on_device.  cell_size <= 0 -> from density.
+  void build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
+             float points_per_cell, cudaStream_t stream);
+  bool ready() const { return ready_; }
+  const GridView& view() const { return view_; }
+  const Info& info() const { return info_; }
+  int n_indexed() const { return view_.n; }
+  int64_t n_points() const { return info_.n_points; }
+  const float4* sorted_points() const { return pts_sorted_.get(); }
+  void reset() { ready_ = false; }
+
+ private:
+  bool ready_ = false;
+  GridView view_{};
+  Info info_{};
+  DevBuf<unsigned char> raw_;
+  DevBuf<float4> pts_unsorted_, pts_sorted_;
+  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, hist_, scan_tmp_;
+  DevBuf<uint32_t> occ_bits_;
+  DevBuf<int> brick_slot_;
+  DevBuf<uint2> cells_, brick_range_;
+  DevBuf<uint32_t> scratch_;  // bbox (6) + counters
+};
+
+// hand-written device-wide primitives (sort_scan.cu)
+// Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  Returns true if the result is in
+// the *_b buffers, false if in *_a.  hist must hold 256 * ceil(n / 2048) + 1024 entries.
+bool radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist,
+                      uint32_t* scan_tmp, int64_t n, int key_bits, cudaStream_t stream);
+size_t radix_sort_hist_entries(int64_t n);
+size_t scan_tmp_entries(int64_t n);
+// exclusive prefix sum of n uint32 (in place allowed); tmp must hold scan_tmp_entries(n)
+void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* tmp, cudaStream_t stream);
+
+}  // namespace gicpb

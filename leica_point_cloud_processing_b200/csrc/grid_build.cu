@@ -1,0 +1,382 @@
+// grid_build.cu - builds the brick-grid spatial index of one cloud on the GPU (see common.cuh).
+//
+// Replaces the FLANN KDTreeSingleIndex builds of pcl::Registration::initCompute / initComputeReciprocal,
+// triggered by gicp_.align() at reference src/GICPAlignment.cpp:96, and the pcl::search::KdTree of
+// Filter::removeFromCloud (reference src/Filter.cpp:181-184).
+//
+// Pipeline (all kernels hand-written, no CUB/Thrust):
+//   ingest   strided xyz -> float4 (x,y,z,id) + bounding box of the finite points (block reduce + atomics)
+//   probe    multi-resolution occupancy bitmaps -> fractal-dimension estimate -> cell size for ~P points/cell
+//   keys     key = brick_linear*512 + morton3(cell in brick); non-finite points get the sentinel key
+//   sort     stable LSD radix sort of (key, id)            (sort_scan.cu)
+//   reorder  gather float4 points into sorted order
+//   tables   brick heads allocate pool slots; cell/brick (begin,end) ranges written by run heads / tails
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace gicpb {
+
+int64_t g_launch_count = 0;
+
+namespace {
+
+constexpr int kProbeLevels = 7;  // 4, 8, ..., 256 cells along the longest axis
+constexpr int kMaxBricks = 1 << 22;
+
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+inline float ord2f(unsigned u) {
+  unsigned b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  std::memcpy(&f, &b, 4);
+  return f;
+}
+
+// scratch layout (uint32): [0..2] min xyz (ordered), [3..5] max xyz (ordered), [6] finite count, [7] slot counter,
+// [8] occupied cell counter
+__global__ void init_scratch_kernel(unsigned* s) {
+  if (threadIdx.x < 3) s[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) s[threadIdx.x] = 0u;
+  else if (threadIdx.x < 16) s[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) ingest_kernel(const unsigned char* __restrict__ raw, int64_t n, int64_t stride,
+                                                      float4* __restrict__ pts, unsigned* __restrict__ scratch) {
+  __shared__ unsigned smin[3][8], smax[3][8], scnt[8];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float x = 0.f, y = 0.f, z = 0.f;
+  bool ok = false;
+  if (i < n) {
+    const float* p = reinterpret_cast<const float*>(raw + i * stride);
+    x = p[0];
+    y = p[1];
+    z = p[2];
+    ok = finite3(x, y, z);
+    pts[i] = make_float4(x, y, z, __int_as_float((int)i));
+  }
+  unsigned mn[3] = {ok ? f2ord(x) : 0xffffffffu, ok ? f2ord(y) : 0xffffffffu, ok ? f2ord(z) : 0xffffffffu};
+  unsigned mx[3] = {ok ? f2ord(x) : 0u, ok ? f2ord(y) : 0u, ok ? f2ord(z) : 0u};
+  unsigned c = ok ? 1u : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = min(mn[a], __shfl_xor_sync(kFullMask, mn[a], o));
+      mx[a] = max(mx[a], __shfl_xor_sync(kFullMask, mx[a], o));
+    }
+    c += __shfl_xor_sync(kFullMask, c, o);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    for (int a = 0; a < 3; ++a) {
+      smin[a][warp] = mn[a];
+      smax[a][warp] = mx[a];
+    }
+    scnt[warp] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned lo = 0xffffffffu, hi = 0u;
+    for (int w = 0; w < 8; ++w) {
+      lo = min(lo, smin[threadIdx.x][w]);
+      hi = max(hi, smax[threadIdx.x][w]);
+    }
+    atomicMin(&scratch[threadIdx.x], lo);
+    atomicMax(&scratch[3 + threadIdx.x], hi);
+  }
+  if (threadIdx.x == 3) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += scnt[w];
+    if (t) atomicAdd(&scratch[6], t);
+  }
+}
+
+struct ProbeParams {
+  float ox, oy, oz;
+  float inv_cell[kProbeLevels];
+  int dim[kProbeLevels];            // cells per axis (cubic bitmaps of dim^3 bits)
+  unsigned long long word_off[kProbeLevels];
+};
+
+__global__ void __launch_bounds__(256) probe_kernel(const float4* __restrict__ pts, int64_t n, ProbeParams pp,
+                                                     unsigned* __restrict__ bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  if (!finite3(p.x, p.y, p.z)) return;
+#pragma unroll
+  for (int l = 0; l < kProbeLevels; ++l) {
+    const int d = pp.dim[l];
+    const int cx = clampi(__float2int_rd((p.x - pp.ox) * pp.inv_cell[l]), 0, d - 1);
+    const int cy = clampi(__float2int_rd((p.y - pp.oy) * pp.inv_cell[l]), 0, d - 1);
+    const int cz = clampi(__float2int_rd((p.z - pp.oz) * pp.inv_cell[l]), 0, d - 1);
+    const unsigned long long bit = ((unsigned long long)cz * d + cy) * d + cx;
+    const unsigned mask = 1u << (bit & 31);
+    unsigned* w = bits + pp.word_off[l] + (bit >> 5);
+    if (!(*w & mask)) atomicOr(w, mask);
+  }
+}
+
+__global__ void __launch_bounds__(256) popcount_kernel(const unsigned* __restrict__ bits, ProbeParams pp,
+                                                        unsigned long long total_words, unsigned* __restrict__ out) {
+  // out[l] += popcount of level l's words
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_words) return;
+  int l = 0;
+#pragma unroll
+  for (int k = 1; k < kProbeLevels; ++k)
+    if (i >= pp.word_off[k]) l = k;
+  const unsigned c = __popc(bits[i]);
+  if (c) atomicAdd(&out[l], c);
+}
+
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ pts, int64_t n, GridView g,
+                                                    uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                    uint32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  uint32_t key = sentinel;
+  if (finite3(p.x, p.y, p.z)) {
+    const int cx = clampi(cell_of(p.x, g.ox, g.inv_h), 0, g.nx - 1);
+    const int cy = clampi(cell_of(p.y, g.oy, g.inv_h), 0, g.ny - 1);
+    const int cz = clampi(cell_of(p.z, g.oz, g.inv_h), 0, g.nz - 1);
+    const uint32_t b = (uint32_t)brick_index(g, cx >> kBrickShift, cy >> kBrickShift, cz >> kBrickShift);
+    key = b * kBrickCells + local_code(cx & 7, cy & 7, cz & 7);
+  }
+  keys[i] = key;
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals,
+                                                       int64_t n, float4* __restrict__ sorted) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sorted[i] = pts[vals[i]];
+}
+
+// brick heads: allocate a pool slot per occupied brick and record where the brick's points begin
+__global__ void __launch_bounds__(256) brick_heads_kernel(const uint32_t* __restrict__ keys, int n_valid,
+                                                           int* __restrict__ brick_slot, unsigned* __restrict__ scratch,
+                                                           uint32_t* __restrict__ brick_begin_tmp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  const uint32_t b = keys[i] >> 9;
+  if (i == 0 || (keys[i - 1] >> 9) != b) {
+    const int slot = (int)atomicAdd(&scratch[7], 1u);
+    brick_slot[b] = slot;
+    brick_begin_tmp[b] = (uint32_t)i;
+  }
+}
+
+__global__ void __launch_bounds__(256) tables_kernel(const uint32_t* __restrict__ keys, int n_valid,
+                                                      const int* __restrict__ brick_slot,
+                                                      const uint32_t* __restrict__ brick_begin_tmp,
+                                                      uint2* __restrict__ cells, uint2* __restrict__ brick_range,
+                                                      unsigned* __restrict__ scratch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_valid) return;
+  const uint32_t k = keys[i];
+  const uint32_t b = k >> 9;
+  const bool last = (i == n_valid - 1);
+  const uint32_t kn = last ? 0xffffffffu : keys[i + 1];
+  const bool head = (i == 0) || (keys[i - 1] != k);
+  const bool tail = last || (kn != k);
+  const int slot = brick_slot[b];
+  uint2* cell = &cells[(size_t)slot * kBrickCells + (k & 511u)];
+  if (head) cell->x = (uint32_t)i;
+  if (tail) cell->y = (uint32_t)i + 1u;
+  if (last || (kn >> 9) != b) brick_range[slot] = make_uint2(brick_begin_tmp[b], (uint32_t)i + 1u);
+  if (head) atomicAdd(&scratch[8], 1u);
+}
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
+                      float points_per_cell, cudaStream_t stream) {
+  const auto t_begin = std::chrono::steady_clock::now();
+  ready_ = false;
+  if (n <= 0) throw ArgError("cloud is empty");
+  if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) throw ArgError("stride must be a multiple of 4 and >= 12");
+  if (raw == nullptr) throw ArgError("null cloud pointer");
+  info_ = Info{};
+  info_.n_points = n;
+
+  // ---- ingest ---------------------------------------------------------------------------------------
+  const unsigned char* d_raw = static_cast<const unsigned char*>(raw);
+  if (!on_device) {
+    raw_.reserve((size_t)n * stride_bytes);
+    GICPB_CUDA(cudaMemcpyAsync(raw_.get(), raw, (size_t)(n - 1) * stride_bytes + 12, cudaMemcpyHostToDevice, stream));
+    d_raw = raw_.get();
+  }
+  pts_unsorted_.reserve(n);
+  pts_sorted_.reserve(n);
+  scratch_.reserve(64);
+  init_scratch_kernel<<<1, 32, 0, stream>>>(scratch_.get());
+  GICPB_LAUNCHED();
+  ingest_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(d_raw, n, stride_bytes, pts_unsorted_.get(), scratch_.get());
+  GICPB_LAUNCHED();
+  unsigned hs[16];
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  GICPB_CUDA(cudaStreamSynchronize(stream));
+  const int64_t n_valid = hs[6];
+  info_.n_indexed = n_valid;
+  if (n_valid == 0) throw ArgError("cloud has no finite point");
+  float bmin[3], bmax[3], ext[3];
+  for (int a = 0; a < 3; ++a) {
+    bmin[a] = ord2f(hs[a]);
+    bmax[a] = ord2f(hs[3 + a]);
+    ext[a] = bmax[a] - bmin[a];
+    info_.bbox_min[a] = bmin[a];
+    info_.bbox_max[a] = bmax[a];
+  }
+  const float lmax = std::max(ext[0], std::max(ext[1], ext[2]));
+  float max_abs = 0.f;
+  for (int a = 0; a < 3; ++a) max_abs = std::max(max_abs, std::max(std::fabs(bmin[a]), std::fabs(bmax[a])));
+
+  // ---- cell size ------------------------------------------------------------------------------------
+  float h = cell_size;
+  if (!(h > 0.f)) {
+    if (!(lmax > 0.f)) {
+      h = 1.0f;
+    } else {
+      ProbeParams pp{};
+      pp.ox = bmin[0];
+      pp.oy = bmin[1];
+      pp.oz = bmin[2];
+      unsigned long long words = 0;
+      for (int l = 0; l < kProbeLevels; ++l) {
+        const int d = 4 << l;
+        pp.dim[l] = d;
+        pp.inv_cell[l] = (float)d / (lmax * 1.0001f);
+        pp.word_off[l] = words;
+        words += ((unsigned long long)d * d * d + 31) / 32;
+      }
+      occ_bits_.reserve(words + 16);
+      GICPB_CUDA(cudaMemsetAsync(occ_bits_.get(), 0, (words + 16) * sizeof(uint32_t), stream));
+      probe_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, pp, occ_bits_.get());
+      GICPB_LAUNCHED();
+      popcount_kernel<<<blocks_for((int64_t)words, 256), 256, 0, stream>>>(occ_bits_.get(), pp, words,
+                                                                           occ_bits_.get() + words);
+      GICPB_LAUNCHED();
+      unsigned occ[kProbeLevels];
+      GICPB_CUDA(cudaMemcpyAsync(occ, occ_bits_.get() + words, sizeof(occ), cudaMemcpyDeviceToHost, stream));
+      GICPB_CUDA(cudaStreamSynchronize(stream));
+      const double N = (double)n_valid;
+      const double tau = points_per_cell > 0.f ? points_per_cell : 3.0;
+      int ls = -1;  // finest level whose cells are still well populated
+      for (int l = 0; l < kProbeLevels; ++l)
+        if (occ[l] > 0 && N / occ[l] >= 8.0) ls = l;
+      if (ls < 0) {
+        h = (float)(lmax / std::max(1.0, std::cbrt(N / tau)));
+      } else {
+        double d = 2.0;
+        if (ls >= 1 && occ[ls - 1] > 0) d = std::log2((double)occ[ls] / (double)occ[ls - 1]);
+        d = std::min(3.0, std::max(1.0, d));
+        const double H = lmax / (double)(4 << ls);
+        const double ratio = std::min(1.0, tau * occ[ls] / N);
+        h = (float)(H * std::pow(ratio, 1.0 / d));
+      }
+    }
+  }
+  if (!(h > 0.f) || !std::isfinite(h)) h = 1.0f;
+  h = std::max(h, lmax / 60000.0f);
+  int dims[3], bd[3];
+  for (;;) {
+    int64_t nb = 1;
+    for (int a = 0; a < 3; ++a) {
+      dims[a] = (int)std::floor(ext[a] / h) + 1;
+      bd[a] = (dims[a] + 7) / 8;
+      dims[a] = bd[a] * 8;
+      nb *= bd[a];
+    }
+    if (nb <= kMaxBricks) break;
+    h *= 1.2f;
+  }
+  const int64_t n_bricks = (int64_t)bd[0] * bd[1] * bd[2];
+  const int maxdim = std::max(dims[0], std::max(dims[1], dims[2]));
+
+  GridView g{};
+  g.ox = bmin[0];
+  g.oy = bmin[1];
+  g.oz = bmin[2];
+  g.h = h;
+  g.inv_h = 1.0f / h;
+  g.margin = h * (0.002f + 5e-7f * (float)maxdim) + 4e-6f * max_abs;
+  g.nx = dims[0];
+  g.ny = dims[1];
+  g.nz = dims[2];
+  g.nbx = bd[0];
+  g.nby = bd[1];
+  g.nbz = bd[2];
+  g.n = (int)n_valid;
+
+  // ---- keys + sort + reorder --------------------------------------------------------------------------
+  keys_a_.reserve(n);
+  keys_b_.reserve(n);
+  vals_a_.reserve(n);
+  vals_b_.reserve(n);
+  hist_.reserve(radix_sort_hist_entries(n));
+  scan_tmp_.reserve(scan_tmp_entries(std::max<int64_t>((int64_t)radix_sort_hist_entries(n), n)));
+  const uint32_t sentinel = (uint32_t)(n_bricks * kBrickCells);
+  int key_bits = 1;
+  while ((1ull << key_bits) <= (unsigned long long)sentinel) ++key_bits;
+  keys_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, g, sentinel, keys_a_.get(),
+                                                      vals_a_.get());
+  GICPB_LAUNCHED();
+  const bool in_b = radix_sort_pairs(keys_a_.get(), vals_a_.get(), keys_b_.get(), vals_b_.get(), hist_.get(),
+                                     scan_tmp_.get(), n, key_bits, stream);
+  const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
+  const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
+  reorder_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, pts_sorted_.get());
+  GICPB_LAUNCHED();
+
+  // ---- brick / cell tables ----------------------------------------------------------------------------
+  brick_slot_.reserve(n_bricks);
+  GICPB_CUDA(cudaMemsetAsync(brick_slot_.get(), 0xff, (size_t)n_bricks * sizeof(int), stream));
+  uint32_t* brick_begin_tmp = in_b ? keys_a_.get() : keys_b_.get();  // the other key buffer is free now
+  if ((int64_t)keys_a_.capacity() < n_bricks) {                      // more bricks than points: dedicated buffer
+    hist_.reserve(std::max<size_t>(hist_.capacity(), (size_t)n_bricks));
+    brick_begin_tmp = hist_.get();
+  }
+  brick_heads_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, brick_slot_.get(),
+                                                                    scratch_.get(), brick_begin_tmp);
+  GICPB_LAUNCHED();
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  GICPB_CUDA(cudaStreamSynchronize(stream));
+  const int64_t n_slots = hs[7];
+  cells_.reserve((size_t)n_slots * kBrickCells);
+  brick_range_.reserve(n_slots);
+  GICPB_CUDA(cudaMemsetAsync(cells_.get(), 0, (size_t)n_slots * kBrickCells * sizeof(uint2), stream));
+  tables_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, brick_slot_.get(), brick_begin_tmp,
+                                                               cells_.get(), brick_range_.get(), scratch_.get());
+  GICPB_LAUNCHED();
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  GICPB_CUDA(cudaStreamSynchronize(stream));
+
+  g.pts = pts_sorted_.get();
+  g.brick_slot = brick_slot_.get();
+  g.cells = cells_.get();
+  g.brick_range = brick_range_.get();
+  view_ = g;
+  info_.cell_size = h;
+  info_.dims[0] = dims[0];
+  info_.dims[1] = dims[1];
+  info_.dims[2] = dims[2];
+  info_.n_bricks_occupied = n_slots;
+  info_.n_cells_occupied = hs[8];
+  info_.ms_build =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  ready_ = true;
+}
+
+}  // namespace gicpb

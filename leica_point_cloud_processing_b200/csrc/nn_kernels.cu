@@ -1,0 +1,309 @@
+// nn_kernels.cu - nearest-neighbour kernels on the brick grid: the per-outer-iteration correspondence pass
+// (transform, exact NN-1, distance gate, Mahalanobis matrix), the fitness score, the cloud difference, the raw
+// NN-1 test hook and the cloud transform.
+//
+// Reference loops replaced (PCL 1.8.1 behind the reference's call sites):
+//   correspondence_kernel  GICP::computeTransformation inner `for i < N` loop (gicp.hpp), reached from
+//                          gicp_.align() at reference src/GICPAlignment.cpp:96,116
+//   fitness_kernel         Registration::getFitnessScore, reference src/GICPAlignment.cpp:103,123
+//   difference_kernel      pcl::getPointCloudDifference, reference src/Filter.cpp:176-189
+//   transform_kernel       pcl::transformPointCloud, reference src/GICPAlignment.cpp:146
+#include <climits>
+
+#include "kernels.hpp"
+
+namespace gicpb {
+
+namespace {
+
+__device__ __forceinline__ NNState nn_init(float gate2) {
+  NNState s;
+  if (gate2 > 0.f) {
+    s.best = gate2;  // strict '<' gate: nothing ties with the sentinel because its index is -1
+    s.pos = -1;
+    s.oi = -1;
+  } else {
+    s.best = __int_as_float(0x7f800000);
+    s.pos = -1;
+    s.oi = INT_MAX;
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(128) nn1_kernel(GridView g, const float4* __restrict__ queries, int n, Rigid T,
+                                                   float gate2, int* __restrict__ idx, float* __restrict__ d2,
+                                                   int* __restrict__ pos_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&queries[i]);
+  NNState s = nn_init(gate2);
+  if (finite3(p.x, p.y, p.z)) {
+    const float3 q = xform(T, p.x, p.y, p.z);
+    if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
+  }
+  if (idx) idx[i] = s.pos >= 0 ? s.oi : -1;
+  if (d2) d2[i] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
+  if (pos_out) pos_out[i] = s.pos;
+}
+
+// One thread per source point of this rank's shard [lo, hi) (sorted source order).
+template <typename MT, bool kUsePrev>
+__global__ void __launch_bounds__(128)
+correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T, RotD R, float gate2,
+                      const double* __restrict__ n_src, const double* __restrict__ n_tgt, double eps,
+                      int* __restrict__ pair_pos, float* __restrict__ pair_d2, float4* __restrict__ pair_tgt,
+                      MT* __restrict__ maha) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = lo + t;
+  if (i >= hi) return;
+  const float4 p = __ldg(&src[i]);
+  const float3 q = xform(T, p.x, p.y, p.z);
+  NNState s = nn_init(gate2);
+  if (kUsePrev) {
+    const int prev = pair_pos[t];
+    if (prev >= 0) {
+      const float4 c = __ldg(&g.pts[prev]);
+      const float d = dist2(q.x, q.y, q.z, c);
+      const int oi = __float_as_int(c.w);
+      if (cand_less(d, oi, s.best, s.oi)) {
+        s.best = d;
+        s.pos = prev;
+        s.oi = oi;
+      }
+    }
+  }
+  if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
+  pair_pos[t] = s.pos;
+  pair_d2[t] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
+  if (s.pos < 0) {
+    pair_tgt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4 c = __ldg(&g.pts[s.pos]);
+  pair_tgt[t] = make_float4(c.x, c.y, c.z, 1.0f);
+
+  // M = (R C1 R^T + C2)^-1 in double, C = I - (1 - eps) n n^T  (gicp.hpp: M = R*C1; temp = M*R^T; temp += C2)
+  const double a = 1.0 - eps;
+  const double sx = n_src[3 * (size_t)t], sy = n_src[3 * (size_t)t + 1], sz = n_src[3 * (size_t)t + 2];
+  const double tx = n_tgt[3 * (size_t)s.pos], ty = n_tgt[3 * (size_t)s.pos + 1], tz = n_tgt[3 * (size_t)s.pos + 2];
+  double C1[9] = {1.0 - a * sx * sx, -a * sx * sy, -a * sx * sz, -a * sy * sx, 1.0 - a * sy * sy, -a * sy * sz,
+                  -a * sz * sx, -a * sz * sy, 1.0 - a * sz * sz};
+  double RC[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      RC[3 * r + cc] = R.m[3 * r] * C1[cc] + R.m[3 * r + 1] * C1[3 + cc] + R.m[3 * r + 2] * C1[6 + cc];
+  double A[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      A[3 * r + cc] = RC[3 * r] * R.m[3 * cc] + RC[3 * r + 1] * R.m[3 * cc + 1] + RC[3 * r + 2] * R.m[3 * cc + 2];
+  A[0] += 1.0 - a * tx * tx; A[1] += -a * tx * ty;      A[2] += -a * tx * tz;
+  A[3] += -a * ty * tx;      A[4] += 1.0 - a * ty * ty; A[5] += -a * ty * tz;
+  A[6] += -a * tz * tx;      A[7] += -a * tz * ty;      A[8] += 1.0 - a * tz * tz;
+  // adjugate inverse (Eigen's fixed-size 3x3 path)
+  const double c00 = A[4] * A[8] - A[5] * A[7];
+  const double c01 = A[2] * A[7] - A[1] * A[8];
+  const double c02 = A[1] * A[5] - A[2] * A[4];
+  const double c10 = A[5] * A[6] - A[3] * A[8];
+  const double c11 = A[0] * A[8] - A[2] * A[6];
+  const double c12 = A[2] * A[3] - A[0] * A[5];
+  const double c20 = A[3] * A[7] - A[4] * A[6];
+  const double c21 = A[1] * A[6] - A[0] * A[7];
+  const double c22 = A[0] * A[4] - A[1] * A[3];
+  const double inv = 1.0 / (A[0] * c00 + A[1] * c10 + A[2] * c20);
+  (void)c10; (void)c20; (void)c21;
+  MT* m = maha + 6 * (size_t)t;
+  m[0] = (MT)(c00 * inv);
+  m[1] = (MT)(c01 * inv);
+  m[2] = (MT)(c02 * inv);
+  m[3] = (MT)(c11 * inv);
+  m[4] = (MT)(c12 * inv);
+  m[5] = (MT)(c22 * inv);
+}
+
+// fitness: partial (sum d2, count) per block -> partials[block*2 + {0,1}]
+__global__ void __launch_bounds__(128) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T,
+                                                       double max_range, double* __restrict__ partials) {
+  __shared__ double ssum[4], scnt[4];
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  double sum = 0.0, cnt = 0.0;
+  if (i < hi) {
+    const float4 p = __ldg(&src[i]);
+    const float3 q = xform(T, p.x, p.y, p.z);
+    NNState s = nn_init(0.f);
+    if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
+    if (s.pos >= 0 && (double)s.best <= max_range) {
+      sum = (double)s.best;
+      cnt = 1.0;
+    }
+  }
+  sum = warp_sum(sum);
+  cnt = warp_sum(cnt);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    ssum[warp] = sum;
+    scnt[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    partials[2 * (size_t)blockIdx.x] = (ssum[0] + ssum[1]) + (ssum[2] + ssum[3]);
+    partials[2 * (size_t)blockIdx.x + 1] = (scnt[0] + scnt[1]) + (scnt[2] + scnt[3]);
+  }
+}
+
+// out[c] = sum over rows of partials[row*ncols + c], fixed order (deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nrows, int ncols,
+                                                               double* __restrict__ out) {
+  __shared__ double sm[8];
+  for (int c = 0; c < ncols; ++c) {
+    double v = 0.0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) v += partials[(size_t)r * ncols + c];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += sm[w];
+      out[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// difference: mask[i] = 1 iff point i is finite and no subtract point lies within d2 <= thr (thr_next = the
+// smallest float above thr, so "d2 < thr_next" == "!(d2 > thr)").  Kept count per block -> atomicAdd.
+__global__ void __launch_bounds__(128) difference_kernel(GridView g, const unsigned char* __restrict__ raw, int64_t n,
+                                                          int64_t stride, float thr_next, int always_keep,
+                                                          unsigned char* __restrict__ mask,
+                                                          unsigned long long* __restrict__ kept) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  if (i < n) {
+    const float* p = reinterpret_cast<const float*>(raw + i * stride);
+    const float x = p[0], y = p[1], z = p[2];
+    if (finite3(x, y, z)) {
+      if (always_keep) {
+        keep = true;  // threshold < 0: every finite point with a neighbour is kept
+      } else {
+        NNState s;
+        s.best = thr_next;
+        s.pos = -1;
+        s.oi = -1;
+        keep = !nn_search<true>(g, x, y, z, s);
+      }
+    }
+    mask[i] = keep ? 1 : 0;
+  }
+  const unsigned b = __ballot_sync(kFullMask, keep);
+  __shared__ unsigned sc[4];
+  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = __popc(b);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = sc[0] + sc[1] + sc[2] + sc[3];
+    if (t) atomicAdd(kept, (unsigned long long)t);
+  }
+}
+
+// xyz <- T * xyz for strided points; the other bytes of each point are copied (4-byte words).  in == out is allowed:
+// every thread reads its own point completely before it writes it.
+__global__ void __launch_bounds__(256) transform_kernel(const unsigned char* in, unsigned char* out, int64_t n,
+                                                         int64_t stride, Rigid T) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(in + i * stride);
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + i * stride);
+  const float x = __uint_as_float(p[0]), y = __uint_as_float(p[1]), z = __uint_as_float(p[2]);
+  const float3 q = xform(T, x, y, z);
+  if (in != out) {
+    const int words = (int)(stride >> 2);
+    for (int k = 3; k < words; ++k) o[k] = p[k];
+  }
+  o[0] = __float_as_uint(q.x);
+  o[1] = __float_as_uint(q.y);
+  o[2] = __float_as_uint(q.z);
+}
+
+__global__ void __launch_bounds__(256) pack_queries_kernel(const unsigned char* __restrict__ raw, int64_t n,
+                                                            int64_t stride, float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(raw + i * stride);
+  out[i] = make_float4(p[0], p[1], p[2], 0.f);
+}
+
+inline unsigned nblocks(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+void launch_nn1(const GridView& g, const float4* queries, int n, const Rigid& T, float gate2, int* idx, float* d2,
+                int* pos, cudaStream_t stream) {
+  if (n <= 0) return;
+  nn1_kernel<<<nblocks(n, 128), 128, 0, stream>>>(g, queries, n, T, gate2, idx, d2, pos);
+  GICPB_LAUNCHED();
+}
+
+void launch_correspondences(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, const RotD& R,
+                            float gate2, const double* n_src, const double* n_tgt, double eps, int* pair_pos,
+                            float* pair_d2, float4* pair_tgt, void* maha, bool maha_fp32, bool use_prev,
+                            cudaStream_t stream) {
+  const int n = hi - lo;
+  if (n <= 0) return;
+  const unsigned nb = nblocks(n, 128);
+  if (maha_fp32) {
+    if (use_prev)
+      correspondence_kernel<float, true><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos,
+                                                                 pair_d2, pair_tgt, (float*)maha);
+    else
+      correspondence_kernel<float, false><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
+                                                                  pair_pos, pair_d2, pair_tgt, (float*)maha);
+  } else {
+    if (use_prev)
+      correspondence_kernel<double, true><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
+                                                                  pair_pos, pair_d2, pair_tgt, (double*)maha);
+    else
+      correspondence_kernel<double, false><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
+                                                                   pair_pos, pair_d2, pair_tgt, (double*)maha);
+  }
+  GICPB_LAUNCHED();
+}
+
+int fitness_partial_rows(int n) { return (int)nblocks(n, 128); }
+
+void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
+                    double* partials, double* out2, cudaStream_t stream) {
+  const int n = hi - lo;
+  if (n <= 0) {
+    GICPB_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), stream));
+    return;
+  }
+  const unsigned nb = nblocks(n, 128);
+  fitness_kernel<<<nb, 128, 0, stream>>>(g, src, lo, hi, T, max_range, partials);
+  GICPB_LAUNCHED();
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb, 2, out2);
+  GICPB_LAUNCHED();
+}
+
+void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
+                       bool always_keep, unsigned char* mask, unsigned long long* kept, cudaStream_t stream) {
+  if (n <= 0) return;
+  difference_kernel<<<nblocks(n, 128), 128, 0, stream>>>(g, raw, n, stride, thr_next, always_keep ? 1 : 0, mask, kept);
+  GICPB_LAUNCHED();
+}
+
+void launch_transform(const unsigned char* in, unsigned char* out, int64_t n, int64_t stride, const Rigid& T,
+                      cudaStream_t stream) {
+  if (n <= 0) return;
+  transform_kernel<<<nblocks(n, 256), 256, 0, stream>>>(in, out, n, stride, T);
+  GICPB_LAUNCHED();
+}
+
+void launch_pack_queries(const unsigned char* raw, int64_t n, int64_t stride, float4* out, cudaStream_t stream) {
+  if (n <= 0) return;
+  pack_queries_kernel<<<nblocks(n, 256), 256, 0, stream>>>(raw, n, stride, out);
+  GICPB_LAUNCHED();
+}
+
+}  // namespace gicpb

@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's GICP stage classes, on top of the C ABI.
+
+`GICPAlignment` keeps the public surface of the reference class (include/GICPAlignment.h:47-145, behaviour of
+src/GICPAlignment.cpp:23-198): same method names, argument meaning, defaults and quirks, so the reference's own
+tests (test/test_gicp_alignment.cpp) translate line by line.  `remove_from_cloud` mirrors
+Filter::removeFromCloud (src/Filter.cpp:176-189).  The C++ drop-in with identical semantics is
+include/GICPAlignment_b200.hpp.
+
+Clouds are numpy float32 arrays [n, 3] (xyz), [n, 4] or [n, 8] (the 32-byte pcl::PointXYZRGB layout; columns past
+xyz are carried through untouched), or CUDA torch tensors of the same shapes.
+"""
+import logging
+
+import numpy as np
+
+from ._capi import Engine, E_NOT_ENOUGH_CORRESPONDENCES, E_SOLVER, E_TOO_FEW_POINTS
+
+log = logging.getLogger("leica_point_cloud_processing_b200")
+
+
+def _copy(cloud):
+    return cloud.clone() if hasattr(cloud, "clone") else np.array(cloud, copy=True)
+
+
+def is_valid_transform(tf):
+    """Utils::isValidTransform (reference src/Utils.cpp:71-82): no NaN entry."""
+    return not bool(np.isnan(np.asarray(tf)).any())
+
+
+class GICPAlignment:
+    """Fine registration of `source_cloud` onto `target_cloud` with GICP (target first, as the reference ctor)."""
+
+    def __init__(self, target_cloud, source_cloud, use_covariances, device=0, engine=None):
+        # reference src/GICPAlignment.cpp:23-35
+        self.target_cloud_ = target_cloud
+        self.source_cloud_ = source_cloud
+        self.covariances_ = bool(use_covariances)
+        self.tf_epsilon_ = 4e-3
+        self.max_iter_ = 100
+        self.max_corresp_distance_ = 4e-2
+        self.ransac_outlier_th_ = 1.0
+        self.transform_exists_ = False
+        self.fine_tf_ = np.eye(4, dtype=np.float32)
+        self.aligned_cloud_ = None
+        self.backup_cloud_ = None
+        self._engine = engine if engine is not None else Engine(device)
+        self._converged = False
+        self._fitness = None
+        self._inputs_set = False
+        self.last_result = None
+
+    # ---- public surface (include/GICPAlignment.h:63-145) ---------------------------------------------
+    def run(self):
+        self._config_parameters()
+        if self.covariances_:
+            self._apply_covariances()
+        self._fine_alignment()
+        self.applyTFtoCloud(self.source_cloud_)
+
+    def iterate(self):
+        self._iterate_fine_alignment()
+
+    def undo(self):
+        if self.backup_cloud_ is not None:
+            self.aligned_cloud_ = _copy(self.backup_cloud_)
+
+    def getFineTransform(self):
+        if not self.transform_exists_:
+            log.error("No transform yet. Please run algorithm")
+        return self.fine_tf_.copy()
+
+    def getAlignedCloud(self, aligned_cloud=None):
+        """Deep copy of the aligned cloud (reference :156-159).  If `aligned_cloud` is a list it is filled in
+        place (the reference's out-parameter form); the copy is returned either way."""
+        out = _copy(self.aligned_cloud_) if self.aligned_cloud_ is not None else np.zeros((0, 3), np.float32)
+        if isinstance(aligned_cloud, list):
+            aligned_cloud[:] = [out]
+        return out
+
+    def applyTFtoCloud(self, cloud):
+        # reference :144-147: reads `cloud`, writes the INTERNAL aligned cloud; `cloud` itself is untouched
+        self.aligned_cloud_ = self._engine.transform_cloud(self.fine_tf_, cloud)
+
+    def setSourceCloud(self, source_cloud):
+        self.source_cloud_ = source_cloud
+        self._inputs_set = False
+
+    def setTargetCloud(self, target_cloud):
+        self.target_cloud_ = target_cloud
+        self._inputs_set = False
+
+    def setMaxIterations(self, iterations):
+        self.max_iter_ = int(iterations)
+        self._config_parameters()
+
+    def setTfEpsilon(self, tf_epsilon):
+        self.tf_epsilon_ = float(tf_epsilon)
+        self._config_parameters()
+
+    def setMaxCorrespondenceDistance(self, max_corresp_distance):
+        # the reference declares this parameter as `int` (include/GICPAlignment.h:138): fractions are truncated
+        self.max_corresp_distance_ = float(int(max_corresp_distance))
+        self._config_parameters()
+
+    def setRANSACOutlierTh(self, ransac_threshold):
+        # `int` in the reference as well (:145); GICP never uses the RANSAC threshold
+        self.ransac_outlier_th_ = float(int(ransac_threshold))
+        self._config_parameters()
+
+    # ---- additions that do not break the reference surface ------------------------------------------
+    def hasConverged(self):
+        return self._converged
+
+    def getFitnessScore(self):
+        return self._fitness
+
+    # ---- private, mirroring the reference's private methods -------------------------------------------
+    def _config_parameters(self):
+        # reference :48-54
+        self._engine.set_params(max_iterations=self.max_iter_, max_corr_distance=self.max_corresp_distance_,
+                                transformation_epsilon=self.tf_epsilon_)
+
+    def _apply_covariances(self):
+        # reference :56-84.  With PCL 1.8.1, setInputSource / setInputTarget (called right after, :89-90) reset any
+        # covariances set here, so the normal-based covariances never reach the solver; the only
+        # lasting effect upstream is the removal of points whose radius-normal is NaN.  That removal (a radius
+        # neighbour count on the same grid) is the "next" row 8(f)-2 and is not part of this round.
+        log.info("Extract covariances from clouds (dropped by setInputSource/Target, as in PCL 1.8.1)")
+
+    def _fine_alignment(self):
+        # reference :86-109
+        log.info("Perform GICP with %d iterations", self.max_iter_)
+        self._engine.set_source(self.source_cloud_)
+        self._engine.set_target(self.target_cloud_)
+        self._inputs_set = True
+        res = self._engine.align(raise_on_failure=False)
+        self.last_result = res
+        log.info("GICP time: %f s", res["ms_total"] * 1e-3)
+        self._converged = bool(res["converged"])
+        if res["rc"] not in (0, E_NOT_ENOUGH_CORRESPONDENCES, E_SOLVER, E_TOO_FEW_POINTS):
+            raise RuntimeError(f"gicpb_align failed with {res['rc']}")
+        if self._converged:
+            self._fitness = self._engine.fitness(res["transform"])
+            log.info("Converged in %f FitnessScore", self._fitness)
+            self.fine_tf_ = res["transform"].copy()
+            self.transform_exists_ = is_valid_transform(self.fine_tf_)
+        else:
+            log.error("GICP no converge")
+
+    def _iterate_fine_alignment(self):
+        # reference :111-127.  PCL's align() re-solves from the ORIGINAL source at identity with the cached
+        # covariances and overwrites the cloud it is given with final_transformation * source.
+        self.backup_cloud_ = _copy(self.aligned_cloud_) if self.aligned_cloud_ is not None else None
+        log.info("Computing iteration...")
+        if not self._inputs_set:
+            self._engine.set_source(self.source_cloud_)
+            self._engine.set_target(self.target_cloud_)
+            self._inputs_set = True
+        res = self._engine.align(raise_on_failure=False)
+        self.last_result = res
+        self._converged = bool(res["converged"])
+        if self._converged:
+            temp_tf = res["transform"]
+            self.fine_tf_ = (temp_tf @ self.fine_tf_).astype(np.float32)
+            self._fitness = self._engine.fitness(temp_tf)
+            log.info("Converged in %f FitnessScore", self._fitness)
+        else:
+            log.error("GICP no converge")
+        self.aligned_cloud_ = self._engine.transform_cloud(res["transform"], self.source_cloud_)
+
+
+def remove_from_cloud(input_cloud, subtract_cloud, threshold, engine=None, device=0):
+    """Filter::removeFromCloud (reference src/Filter.cpp:176-189): the points of `input_cloud` whose SQUARED
+    distance to their nearest neighbour in `subtract_cloud` exceeds `threshold`, in input order.
+    Returns (filtered_cloud, mask)."""
+    eng = engine if engine is not None else Engine(device)
+    log.info("Difference from segment with threshold: %f", threshold)
+    mask, _ = eng.cloud_difference(input_cloud, subtract_cloud, threshold)
+    keep = mask.bool() if hasattr(mask, "bool") else mask.astype(bool)
+    return input_cloud[keep], mask
