@@ -107,9 +107,12 @@ def add_fod_blobs(cloud, n_blobs=20, seed=999, length=4.0, width=2.0, radius=3.0
 
 
 def rotation_error_rad(Ta, Tb):
+    """Angle of Ra^T Rb, from atan2 of the skew part and the trace (well conditioned near zero, unlike acos)."""
     Ra, Rb = np.asarray(Ta, np.float64)[:3, :3], np.asarray(Tb, np.float64)[:3, :3]
-    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
-    return float(np.arccos(np.clip(c, -1.0, 1.0)))
+    M = Ra.T @ Rb
+    s = 0.5 * np.linalg.norm([M[2, 1] - M[1, 2], M[0, 2] - M[2, 0], M[1, 0] - M[0, 1]])
+    c = 0.5 * (np.trace(M) - 1.0)
+    return float(np.arctan2(s, c))
 
 
 def translation_error(Ta, Tb):

@@ -341,6 +341,8 @@ def test_reference_testRunWithCov(cube_pair):
     assert g.transform_exists_
     # iterate() re-solves from the original source and left-multiplies the same transform
     assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)
-    before = g.getAlignedCloud()
+    # PCL's align() overwrote the cloud with T_new * source; undo() restores the pre-iterate copy (reference :139-142)
+    g.aligned_cloud_ = g.aligned_cloud_ + np.float32(1.0)
     g.undo()
-    assert not np.array_equal(before, g.getAlignedCloud()) or np.array_equal(T1, np.eye(4))
+    assert np.array_equal(g.getAlignedCloud(), g.backup_cloud_)
+    assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)  # fine_tf_ is NOT rolled back, as upstream
