@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py - GICP hot path benchmark (BASELINE.json metric: GICP correspondences/s and align ms).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA engine (N > 1: under torchrun)
+    python bench.py --impl reference --gpus N ...           # the reference's CPU algorithm (oracle, all host threads)
+
+A step = one complete registration job on one synthetic pair (SURVEY section 8d config 2 at N = 1: 1 M-point noisy
+scan vs 1 M-point CAD cloud of the aircraft-panel surface, 5 deg / 2 cm initial offset, gate 1 m): index both clouds,
+kNN-20 covariances, the GICP outer loop to convergence, fitness score.  `value` is measured with the raw clouds
+already resident in HBM; `e2e` goes through the same C-ABI calls with pinned HOST buffers, so the host->device copy
+of both clouds and the read-back of the transform and fitness are inside the timed region.
+value = (source queries answered by the correspondence kernel over all outer iterations, all ranks) / step time.
+N > 1: source sharded by rank (weak scaling: 1 M source AND target points per GPU), target replicated, one NCCL
+all-reduce of 14 doubles per cost evaluation.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GATE_M = 1.0  # config 2: the only integer gate reachable through setMaxCorrespondenceDistance(int) that holds 20 cm
+
+
+def workload_points(n_gpus, override):
+    return override if override else 1_000_000 * n_gpus
+
+
+def make_clouds(n):
+    from leica_point_cloud_processing_b200 import synth
+    length, width = (4.0, 2.0) if n <= 2_000_000 else (12.0, 4.0)
+    if n > 2_000_000:
+        # scale the patch with the point count so the ~2-3 mm sampling density of config 3 is kept
+        s = (n / 10_000_000) ** 0.5
+        length, width = 12.0 * s, 4.0 * s
+    src, tgt, T_star = synth.make_pair(n, n, length=length, width=width)
+    return src, tgt, T_star, (length, width)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            parts = [p.strip() for p in l.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU algorithm for this path (oracle restatement of PCL 1.8.1 GICP; PCL itself cannot be
+    built in this image), all host threads, same workload generator, bounded in size."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.oracle import Oracle, default_params
+    orc = Oracle(fast=True)
+    n_full = workload_points(args.gpus, args.points)
+    n = min(n_full, args.ref_points)
+    src, tgt, T_star, dims = make_clouds(n)
+    prm = default_params(max_corr_distance=GATE_M)
+    times, queries, outer = [], 0, 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = orc.align(src, tgt, prm)
+        orc.fitness(src, tgt, r["T"])
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            queries += r["n_corr_queries"]
+            outer = r["outer_iterations"]
+    total = sum(times)
+    value = queries / total
+    sample = (f"full workload: {n} source x {n} target points" if n == n_full else
+              f"{n} source x {n} target points of the same generator (workload is {n_full}); whole job per step")
+    line = {
+        "impl": "reference", "metric": "gicp_correspondences_per_s", "value": value, "unit": "correspondences/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / f64 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"aircraft-panel {n_full} src vs {n_full} tgt, 5deg/2cm offset, gate {GATE_M} m",
+                   "outer_iterations": outer},
+        "cpu_baseline": {"value": value, "unit": "correspondences/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "correspondences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from leica_point_cloud_processing_b200 import Engine
+    from leica_point_cloud_processing_b200.distributed import env_rank_world, init_engine_comm
+
+    rank, world, local_rank = env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = workload_points(world, args.points)
+    src, tgt, T_star, dims = make_clouds(n)
+    h_src = torch.from_numpy(src).pin_memory()
+    h_tgt = torch.from_numpy(tgt).pin_memory()
+    d_src = h_src.cuda()
+    d_tgt = h_tgt.cuda()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    eng = Engine(local_rank)
+    init_engine_comm(eng, rank, world)
+    eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32)
+
+    def step(tgt_buf, src_buf):
+        eng.set_target(tgt_buf)
+        eng.set_source(src_buf)
+        res = eng.align()
+        fit = eng.fitness(res["transform"])
+        return res, fit
+
+    def timed(tgt_buf, src_buf, steps, warmup):
+        for _ in range(warmup):
+            flush.zero_()
+            step(tgt_buf, src_buf)
+        times, last, queries, ms_corr, n_corr_launch = [], None, 0, 0.0, 0
+        for _ in range(steps):
+            flush.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            res, fit = step(tgt_buf, src_buf)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            times.append(max_over_ranks(dt))
+            queries += res["corr_queries"]
+            ms_corr += res["ms_corr"]
+            n_corr_launch += res["outer_iterations"]
+            last = (res, fit)
+        return times, last, queries, ms_corr, n_corr_launch
+
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count()
+    if rank == 0:
+        sampler.start()
+    times, (res, fit), queries, ms_corr, n_corr_launch = timed(d_tgt, d_src, args.steps, args.warmup)
+    launches = eng.launch_count() - launches0
+    e_times, (e_res, e_fit), e_queries, _, _ = timed(h_tgt, h_src, args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-phase view of one more (untimed) step, for the roofline objects
+    flush.zero_()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); eng.set_target(d_tgt); t_tgt = time.perf_counter() - t0
+    t0 = time.perf_counter(); eng.set_source(d_src); t_src = time.perf_counter() - t0
+    t0 = time.perf_counter(); eng.compute_covariances(); t_cov = time.perf_counter() - t0
+    t0 = time.perf_counter(); pres = eng.align(); t_align = time.perf_counter() - t0
+    t0 = time.perf_counter(); eng.fitness(pres["transform"]); t_fit = time.perf_counter() - t0
+    T_fin = pres["transform"]
+    ms_corr_k, _ = eng.bench_kernel(0, T_fin, iters=10)   # correspondence pass at the converged pose (no seeding)
+    ms_nn_k, _ = eng.bench_kernel(2, T_fin, iters=10)     # NN-1 only
+    ms_cost_k, _ = eng.bench_kernel(1, T_fin, iters=20)   # cost/gradient evaluation
+    ginfo = eng.grid_info(0)
+
+    peak, peak_src = measured_hbm_peak()
+    n_shard = n // world
+    total = sum(times)
+    value = queries / total
+    e_total = sum(e_times)
+    e2e_value = e_queries / e_total
+    # dominant kernel of the recurring loop: the correspondence pass.  Algorithmic bytes per launch:
+    # 96 B per source point of this rank + 16 B per target point.
+    corr_bytes = 96.0 * n_shard + 16.0 * n
+    corr_ms_live = ms_corr / max(n_corr_launch, 1)
+    achieved = corr_bytes / (corr_ms_live * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "correspondence_kernel (NN-1 + gate + Mahalanobis)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": corr_bytes, "ms_per_launch": corr_ms_live,
+                "launches_timed": n_corr_launch}
+    cost_bytes = (56.0 if args.maha_fp32 else 80.0) * n_shard
+    extra = {
+        "phases_ms": {"index_target": 1e3 * t_tgt, "index_source": 1e3 * t_src, "covariances": 1e3 * t_cov,
+                      "align": 1e3 * t_align, "fitness": 1e3 * t_fit, "align_corr_kernel_total": pres["ms_corr"],
+                      "align_cost_evals_total": pres["ms_cost"], "cost_evaluations": pres["cost_evaluations"],
+                      "outer_iterations": pres["outer_iterations"]},
+        "kernels": {
+            "correspondence_cold_ms": ms_corr_k,
+            "correspondence_GBps_algorithmic": corr_bytes / (ms_corr_k * 1e-3) / 1e9,
+            "nn1_only_ms": ms_nn_k,
+            "nn1_GBps_algorithmic": (24.0 * n_shard + 16.0 * n) / (ms_nn_k * 1e-3) / 1e9,
+            "cost_eval_ms": ms_cost_k,
+            "cost_GBps_algorithmic": cost_bytes / (ms_cost_k * 1e-3) / 1e9,
+        },
+        "grid": {"cell_size_m": ginfo["cell_size"], "dims": ginfo["dims"], "bricks": ginfo["n_bricks_occupied"],
+                 "cells_occupied": ginfo["n_cells_occupied"],
+                 "points_per_cell": ginfo["n_indexed"] / max(ginfo["n_cells_occupied"], 1)},
+    }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from leica_point_cloud_processing_b200 import synth
+        from oracle.oracle import Oracle, default_params
+        orc = Oracle(fast=True)
+        nb = min(n, args.cpu_points)
+        bs, bt = (src, tgt) if nb == n else synth.make_pair(nb, nb, length=dims[0], width=dims[1])[:2]
+        t0 = time.perf_counter()
+        r = orc.align(bs, bt, default_params(max_corr_distance=GATE_M))
+        orc.fitness(bs, bt, r["T"])
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": r["n_corr_queries"] / dt, "unit": "correspondences/s", "cores": orc.num_threads(),
+                        "kind": "port", "seconds": dt,
+                        "sample": (f"one whole job on {nb} src x {nb} tgt points of the same generator"
+                                   + ("" if nb == n else f" (workload is {n})")),
+                        "outer_iterations": r["outer_iterations"]}
+        # parity spot check on the benchmark workload itself (not timed)
+        if nb == n:
+            extra["parity_vs_oracle"] = {"rot_rad": synth.rotation_error_rad(res["transform"], r["T"]),
+                                         "trans_m": synth.translation_error(res["transform"], r["T"]),
+                                         "outer_gpu": res["outer_iterations"], "outer_cpu": r["outer_iterations"]}
+
+    if rank == 0:
+        h2d = int(src.nbytes + tgt.nbytes)
+        line = {
+            "metric": "gicp_correspondences_per_s", "value": value, "unit": "correspondences/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 search / f64 accumulate", "data": "synthetic",
+            "config": {"workload": f"aircraft-panel {n} src vs {n} tgt, 5deg/2cm offset, gate {GATE_M} m "
+                                   f"(SURVEY 8d config 2{' x N, weak' if world > 1 else ''})",
+                       "points_source": n, "points_target": n, "sharding": f"source/{world}, target replicated",
+                       "l2": "256 MiB flush write between timed steps", "timing": "wall clock between device syncs, "
+                       "max over ranks (the step contains the host BFGS loop); kernels by CUDA events on the engine stream",
+                       "mahalanobis": "fp32" if args.maha_fp32 else "fp64",
+                       "outer_iterations": res["outer_iterations"], "cost_evaluations": res["cost_evaluations"]},
+            "align_ms": res["ms_total"], "fitness": fit,
+            "e2e": {"value": e2e_value, "unit": "correspondences/s", "ms_per_step": 1e3 * e_total / len(e_times),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 * 4 + 8 + 14 * 8 * int(e_res["cost_evaluations"])},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "clocks": clocks,
+            "detail": extra,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=0, help="points per cloud (default 1M x gpus)")
+    ap.add_argument("--cpu-points", type=int, default=1_000_000, help="cpu_baseline sample size")
+    ap.add_argument("--ref-points", type=int, default=2_000_000, help="--impl reference sample cap")
+    ap.add_argument("--maha-fp32", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

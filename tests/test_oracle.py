@@ -1,0 +1,152 @@
+"""CPU tests of the oracle (oracle/gicp_oracle.cpp): it is pinned against every fact the reference's own tests and
+fixtures hold for this path and against independent brute-force / numpy checks.
+The reference has no golden transform or fitness value, so these known answers are what anchors the oracle."""
+import numpy as np
+import pytest
+
+from oracle.oracle import default_params
+
+
+def test_cube_fixture_is_the_reference_fixture(oracle, cube_mesh, cube_pair):
+    V, F = cube_mesh
+    assert V.shape == (24, 3) and F.shape == (12, 3)
+    src, tgt, T = cube_pair
+    # reference src/CADToPointCloud.cpp:101-190 with libc rand() never seeded: first three samples
+    golden = np.array([[-0.25599825, 0.01642874, 1.0], [-0.53235954, 0.90960455, -1.0],
+                       [1.0, 0.5130681, 0.75297415]], np.float32)
+    assert np.allclose(src[:3], golden, atol=1e-7)
+    # every sample lies on the surface of the +-1 cube
+    assert np.allclose(np.abs(src).max(axis=1), 1.0, atol=1e-6)
+    # second fixture of the same gtest binary consumes the next 15000 rand() draws
+    src2 = oracle.sample_mesh(V, F, 5000, skip_draws=15000)
+    assert not np.array_equal(src, src2)
+    # Utils::rotateCloud(0, 0, 0.175)  (reference src/Utils.cpp:215-229, test/test_gicp_alignment.cpp:35)
+    assert abs(T[0, 0] - np.cos(0.175)) < 1e-6 and abs(T[1, 0] - np.sin(0.175)) < 1e-6
+    assert np.array_equal(T[2], [0, 0, 1, 0]) and np.array_equal(T[3], [0, 0, 0, 1])
+
+
+def test_fixture_known_answers(oracle, cube_pair):
+    src, tgt, _ = cube_pair
+    assert abs(oracle.resolution(src) - 0.03447) < 1e-5            # Utils::computeCloudResolution
+    idx, d2 = oracle.nn1(tgt, src)
+    assert int((d2 < np.float32(0.04) ** 2).sum()) == 1473         # pairs inside the default 0.04 m gate at identity
+    assert int((d2 < 25.0).sum()) == 5000                          # all inside the 5 m gate of testRun
+    assert abs(d2.astype(np.float64).mean() - 6.33e-3) < 1e-5      # pre-alignment fitness
+    assert abs(oracle.fitness(src, tgt, np.eye(4)) - d2.astype(np.float64).mean()) < 1e-15
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_tree_search_equals_brute_force(oracle, seed):
+    rng = np.random.default_rng(seed)
+    tgt = rng.random((4000, 3)).astype(np.float32)
+    tgt = np.concatenate([tgt, tgt[:300]])      # duplicates -> ties, lowest index must win
+    tgt[17] = np.nan
+    qry = np.concatenate([rng.random((1500, 3)).astype(np.float32) * 3 - 1, tgt[:200]])
+    i1, d1 = oracle.nn1(tgt, qry, use_tree=True)
+    i0, d0 = oracle.nn1(tgt, qry, use_tree=False)
+    assert np.array_equal(i1, i0) and np.array_equal(d1, d0)
+    # independent numpy check of the brute force (float32 arithmetic in the same order)
+    q, t = qry[:50, None, :], tgt[None, :, :]
+    dd = (q - t).astype(np.float32)
+    ref = (dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2]
+    ref[:, 17] = np.inf
+    assert np.array_equal(np.argmin(ref, axis=1), i0[:50])
+    cloud = tgt[:2000].copy()
+    cloud[17] = 0.5
+    k1, kd1 = oracle.knn(cloud, 20, use_tree=True)
+    k0, kd0 = oracle.knn(cloud, 20, use_tree=False)
+    assert np.array_equal(k1, k0) and np.array_equal(kd1, kd0)
+    assert np.array_equal(k1[:, 0], np.where(np.arange(2000) < 0, 0, k1[:, 0]))
+    assert (kd1[:, 0] == 0).all()               # the point itself (or an identical earlier point) is neighbour 0
+
+
+def test_covariances_are_plane_to_plane(oracle, cube_pair):
+    src, _, _ = cube_pair
+    cov = oracle.covariances(src)
+    w, v = np.linalg.eigh(cov)
+    assert np.allclose(w[:, 0], 1e-3, atol=1e-12) and np.allclose(w[:, 1:], 1.0, atol=1e-12)
+    # points well inside the +z face: the epsilon direction is the face normal
+    inner = (src[:, 2] == 1.0) & (np.abs(src[:, 0]) < 0.7) & (np.abs(src[:, 1]) < 0.7)
+    assert inner.sum() > 100
+    assert np.allclose(np.abs(v[inner][:, :, 0]), [0, 0, 1], atol=1e-9)
+    with pytest.raises(RuntimeError):
+        oracle.covariances(src[:10], k=20)      # k > cloud size (gicp.hpp computeCovariances)
+
+
+def test_gradient_matches_finite_differences(oracle, cube_pair):
+    src, tgt, _ = cube_pair
+    cov_s, cov_t = oracle.covariances(src), oracle.covariances(tgt)
+    T = oracle.apply_state([0.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+    cnt, idx, d2, maha = oracle.correspondences(src, tgt, cov_s, cov_t, T, 5.0)
+    valid = np.nonzero(idx >= 0)[0].astype(np.int32)
+    x0 = np.array([0.02, -0.01, 0.03, 0.05, -0.04, 0.1])
+    f0, g = oracle.cost(src, tgt, valid, idx[valid], maha, x0)
+    # the functor transforms points with a FLOAT matrix, so f is only smooth down to ~1e-7: use a wide step
+    h = 1e-3
+    for k in range(6):
+        xp, xm = x0.copy(), x0.copy()
+        xp[k] += h
+        xm[k] -= h
+        fd = (oracle.cost(src, tgt, valid, idx[valid], maha, xp)[0] -
+              oracle.cost(src, tgt, valid, idx[valid], maha, xm)[0]) / (2 * h)
+        assert abs(fd - g[k]) <= 2e-4 * max(1.0, abs(g[k])), (k, fd, g[k])
+
+
+def test_apply_state_roundtrip(oracle):
+    x = np.array([0.1, -0.2, 0.3, 0.2, -0.1, 0.4])
+    T = oracle.apply_state(x).astype(np.float64)
+    assert np.allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-6)
+    assert np.allclose(T[:3, 3], x[:3], atol=1e-7)
+    # Rz(yaw) Ry(pitch) Rx(roll): recover the angles as estimateRigidTransformationBFGS seeds them
+    assert abs(np.arctan2(T[2, 1], T[2, 2]) - x[3]) < 1e-6
+    assert abs(np.arcsin(-T[2, 0]) - x[4]) < 1e-6
+    assert abs(np.arctan2(T[1, 0], T[0, 0]) - x[5]) < 1e-6
+
+
+def test_gicp_recovers_the_fixture_rotation(oracle, cube_pair):
+    """The implied known answer of test/test_gicp_alignment.cpp: T = Rz(0.175 rad)."""
+    from leica_point_cloud_processing_b200 import synth
+    src, tgt, T_true = cube_pair
+    r = oracle.align(src, tgt, default_params(max_corr_distance=5.0, transformation_epsilon=5e-4))  # testRun params
+    assert r["converged"] == 1 and r["n_pairs_last"] == 5000
+    assert synth.rotation_error_rad(r["T"], T_true) <= 1e-4
+    assert synth.translation_error(r["T"], T_true) <= 1e-4
+    r2 = oracle.align(src, tgt)                                                                    # reference defaults
+    assert r2["converged"] == 1
+    assert synth.rotation_error_rad(r2["T"], T_true) <= 1e-4
+    assert oracle.fitness(src, tgt, r2["T"]) < 1e-8
+    # reaching max_iterations counts as converged
+    r3 = oracle.align(src, tgt, default_params(max_iterations=1))
+    assert r3["converged"] == 1 and r3["outer_iterations"] == 1
+    # fewer than 4 correspondences: not converged, transform stays identity (reference src/GICPAlignment.cpp:101-108)
+    r4 = oracle.align(src, tgt + np.float32(50.0), default_params(max_corr_distance=1e-3))
+    assert r4["converged"] == 0 and np.array_equal(r4["T"], np.eye(4, dtype=np.float32))
+
+
+def test_difference_matches_brute_force(oracle, cube_pair):
+    src, tgt, _ = cube_pair
+    rng = np.random.default_rng(2)
+    inp = np.concatenate([tgt[:800] + rng.normal(0, 0.02, (800, 3)).astype(np.float32), tgt[:20]])
+    inp[5] = np.nan
+    for thr in (4e-4, 1.2e-2, 0.0):
+        mask, kept = oracle.difference(inp, tgt, thr)
+        _, d2 = oracle.nn1(tgt, inp, use_tree=False)
+        ref = (d2.astype(np.float64) > thr) & np.isfinite(inp).all(axis=1)
+        assert np.array_equal(mask.astype(bool), ref) and kept == int(ref.sum())
+    # reference test/test_filter.cpp:102-113: cube moved by +2 against the cube keeps more than one point
+    cube = rng.random((2000, 3)).astype(np.float32)
+    mask, kept = oracle.difference(cube + np.float32(2.0), cube, oracle.resolution(cube))
+    assert kept > 1
+
+
+def test_panel_generator_and_oracle_on_noise(oracle):
+    from leica_point_cloud_processing_b200 import synth
+    src, tgt, T_star = synth.make_pair(20000, 20000)
+    assert src.dtype == np.float32 and src.shape == (20000, 3)
+    r = oracle.align(src, tgt, default_params(max_corr_distance=1.0))
+    assert r["converged"] == 1
+    assert synth.rotation_error_rad(r["T"], T_star) < 5e-3
+    assert synth.translation_error(r["T"], T_star) < 1e-2
+    R = T_star[:3, :3]
+    assert abs(synth.rotation_error_rad(np.eye(4), T_star) - np.deg2rad(5.0)) < 1e-9
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12)
