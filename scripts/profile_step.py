@@ -1,0 +1,25 @@
+"""One registration job on the bench workload (plus the isolated-kernel hooks), short enough to run under ncu.
+Usage: python scripts/profile_step.py [points]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from leica_point_cloud_processing_b200 import Engine, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+src, tgt, T_star = synth.make_pair(n, n)
+eng = Engine(0)
+eng.set_params(max_corr_distance=1.0)
+for rep in range(2):
+    eng.set_target(tgt)
+    eng.set_source(src)
+    res = eng.align()
+    fit = eng.fitness(res["transform"])
+ms_corr, _ = eng.bench_kernel(0, res["transform"], iters=3)
+ms_nn, _ = eng.bench_kernel(2, res["transform"], iters=3)
+ms_cost, _ = eng.bench_kernel(1, res["transform"], iters=3)
+mask, kept = eng.cloud_difference(synth.apply_rigid(T_star, src), tgt, 4e-4)
+print("outer", res["outer_iterations"], "evals", res["cost_evaluations"], "ms", res["ms_total"], "fit", fit,
+      "corr_ms", ms_corr, "nn_ms", ms_nn, "cost_ms", ms_cost, "kept", kept, "launches", eng.launch_count())
