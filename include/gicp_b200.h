@@ -64,6 +64,7 @@ typedef struct gicpb_align_result {
   int64_t cost_evaluations;  /* cost/gradient kernel launches                                          */
   int64_t corr_queries;      /* source queries processed by the correspondence kernel (all outer its.) */
   int64_t corr_pairs_last;   /* correspondences of the last outer iteration (all ranks)                */
+  int64_t corr_far_queries;  /* of corr_queries (this rank), those answered by the hierarchical far search */
   double ms_total;           /* wall ms of gicpb_align                                                 */
   double ms_corr;            /* device ms in the correspondence (NN + gate + Mahalanobis) kernel       */
   double ms_cost;            /* device ms in the cost/gradient kernel                                  */
@@ -148,6 +149,9 @@ int gicpb_bench_kernel(gicpb_ctx* ctx, int which, const float transform[16], int
                        int64_t* launches);
 /* number of kernels this library launched since the context was created */
 int64_t gicpb_launch_count(const gicpb_ctx* ctx);
+/* how many queries of the most recent search (NN-1, kNN, correspondence, fitness or difference launch) were
+ * answered by the hierarchical far instance instead of the near one; -1 on error */
+int64_t gicpb_last_far_queries(gicpb_ctx* ctx);
 
 #ifdef __cplusplus
 }

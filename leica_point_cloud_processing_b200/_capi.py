@@ -48,6 +48,7 @@ class AlignResult(ctypes.Structure):
         ("cost_evaluations", ctypes.c_int64),
         ("corr_queries", ctypes.c_int64),
         ("corr_pairs_last", ctypes.c_int64),
+        ("corr_far_queries", ctypes.c_int64),
         ("ms_total", ctypes.c_double),
         ("ms_corr", ctypes.c_double),
         ("ms_cost", ctypes.c_double),
@@ -99,6 +100,7 @@ _SIGNATURES = [
     ("gicpb_grid_info_get", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.POINTER(GridInfo)]),
     ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
+    ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
@@ -359,6 +361,12 @@ class Engine:
         launches = ctypes.c_int64()
         self._check(self.lib.gicpb_bench_kernel(self.h, which, Tp, iters, ctypes.byref(ms), ctypes.byref(launches)))
         return ms.value, int(launches.value)
+
+    def last_far_queries(self):
+        return int(self.lib.gicpb_last_far_queries(self.h))
+
+    def last_far_queries(self):
+        return int(self.lib.gicpb_last_far_queries(self.h))
 
     def launch_count(self):
         return int(self.lib.gicpb_launch_count(self.h))

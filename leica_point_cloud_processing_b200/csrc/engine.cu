@@ -181,9 +181,12 @@ struct gicpb_ctx {
   DevBuf<double> d_sums;          // 16 doubles on the device (NCCL path / fitness)
   double* h_sums = nullptr;       // pinned, mapped
   double* h_sums_dev = nullptr;   // device alias of h_sums
+  unsigned* h_far = nullptr;      // pinned: far-query count of the last correspondence pass
   DevBuf<float4> queries;
   DevBuf<unsigned char> io_a, io_b;
   DevBuf<unsigned long long> counter;
+  DevBuf<unsigned char> far_flags;  // near -> far hand-over (kernels.hpp FarWork)
+  DevBuf<unsigned> far_counter;
 
   NcclApi* nccl = nullptr;
   NcclApi::comm_t comm = nullptr;
@@ -191,6 +194,7 @@ struct gicpb_ctx {
 
   // accounting
   double ms_corr = 0, ms_cost = 0;
+  int64_t far_queries = 0;
   int64_t cost_evals = 0;
 };
 
@@ -242,6 +246,14 @@ void all_reduce_sum(gicpb_ctx* c, double* dev, int count) {
   check_nccl(c, c->nccl->AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream), "ncclAllReduce");
 }
 
+constexpr int kFarBlocksPerSm = 8;
+
+FarWork far_work(gicpb_ctx* c, int64_t n_items, int near_rings = kNearMaxRing) {
+  c->far_flags.reserve((size_t)std::max<int64_t>(n_items, 1) + kFarTile);
+  c->far_counter.reserve(4);
+  return FarWork{c->far_flags.get(), c->far_counter.get(), c->num_sms * kFarBlocksPerSm, near_rings};
+}
+
 void update_shard(gicpb_ctx* c) {
   const int64_t n = c->src.ready() ? c->src.n_indexed() : 0;
   c->shard_lo = (int)(n * c->rank / c->world);
@@ -259,8 +271,9 @@ void ensure_covariances(gicpb_ctx* c) {
   const int ns = c->shard_hi - c->shard_lo;
   c->n_tgt.reserve(3 * (size_t)c->tgt.n_indexed());
   c->n_src.reserve(3 * (size_t)std::max(ns, 1));
-  launch_knn_covariances(c->tgt.view(), 0, c->tgt.n_indexed(), k, c->n_tgt.get(), nullptr, nullptr, c->stream);
-  launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, c->stream);
+  const FarWork fw = far_work(c, std::max(c->tgt.n_indexed(), ns));
+  launch_knn_covariances(c->tgt.view(), 0, c->tgt.n_indexed(), k, c->n_tgt.get(), nullptr, nullptr, fw, c->stream);
+  launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream);
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
   c->cov_ready = true;
   c->pairs_valid = false;
@@ -272,7 +285,7 @@ void ensure_pair_buffers(gicpb_ctx* c) {
   c->pair_d2.reserve(ns);
   c->pair_tgt.reserve(ns);
   c->maha.reserve(6 * ns);
-  c->partials.reserve((size_t)c->num_sms * 4 * kCostSums + 2 * (size_t)fitness_partial_rows((int)ns) + 64);
+  c->partials.reserve((size_t)c->num_sms * 4 * kCostSums + 2 * (size_t)fitness_partial_rows((int)ns, c->num_sms * kFarBlocksPerSm) + 64);
   c->ticket.reserve(4);
   c->d_sums.reserve(16);
 }
@@ -291,8 +304,9 @@ void run_correspondences(gicpb_ctx* c, const float* T16, bool first) {
   GICPB_CUDA(cudaEventRecord(c->ev0, c->stream));
   launch_correspondences(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, R, gate2, c->n_src.get(),
                          c->n_tgt.get(), c->prm.gicp_epsilon, c->pair_pos.get(), c->pair_d2.get(), c->pair_tgt.get(),
-                         c->maha.get(), fp32, use_prev, c->stream);
+                         c->maha.get(), fp32, use_prev, far_work(c, c->shard_hi - c->shard_lo, first ? 1 : kNearMaxRing), c->stream);
   GICPB_CUDA(cudaEventRecord(c->ev1, c->stream));
+  GICPB_CUDA(cudaMemcpyAsync(c->h_far, c->far_counter.get() + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   c->pairs_valid = true;
   c->pairs_fp32 = fp32;
 }
@@ -340,6 +354,7 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
   ensure_pair_buffers(c);
   c->ms_corr = c->ms_cost = 0;
   c->cost_evals = 0;
+  c->far_queries = 0;
 
   float T[16], prev[16];
   identity16(T);
@@ -369,6 +384,7 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
         first_eval = false;
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->ms_corr += ms;
+        c->far_queries += c->h_far[0];
       }
       m_pairs = s[13];
       if (m_pairs < 4.0) return false;  // NotEnoughPointsException (< 4 correspondences)
@@ -417,6 +433,7 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
   out->cost_evaluations = c->cost_evals;
   out->corr_queries = corr_queries;
   out->corr_pairs_last = (int64_t)pairs_last;
+  out->corr_far_queries = c->far_queries;
   out->ms_corr = c->ms_corr;
   out->ms_cost = c->ms_cost;
   out->ms_total = now_ms() - t_begin;
@@ -487,6 +504,7 @@ int gicpb_create(int device, gicpb_ctx** out) {
     GICPB_CUDA(cudaEventCreate(&c->ev1));
     GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
+    GICPB_CUDA(cudaHostAlloc(&c->h_far, 4 * sizeof(unsigned), cudaHostAllocDefault));
     c->ticket.reserve(4);
     GICPB_CUDA(cudaMemset(c->ticket.get(), 0, 4 * sizeof(unsigned)));
     c->counter.reserve(2);
@@ -503,6 +521,7 @@ void gicpb_destroy(gicpb_ctx* c) {
   if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_sums) cudaFreeHost(c->h_sums);
+  if (c->h_far) cudaFreeHost(c->h_far);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -608,7 +627,7 @@ int gicpb_fitness(gicpb_ctx* c, const float transform[16], double max_range, dou
     const Rigid T = rigid_from_rowmajor(transform);
     double* partials = c->partials.get() + (size_t)c->num_sms * 4 * kCostSums;
     launch_fitness(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, max_range, partials,
-                   c->d_sums.get(), c->stream);
+                   c->d_sums.get(), far_work(c, c->shard_hi - c->shard_lo), c->stream);
     all_reduce_sum(c, c->d_sums.get(), 2);
     GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -651,6 +670,7 @@ int gicpb_difference_run(gicpb_ctx* c, const void* input, int64_t n, int64_t str
     if (!mask) throw ArgError("null mask");
     check_cloud_args(input, n, stride);
     if (!c->sub.ready()) throw StateError("difference_set_subtract must be called first");
+    if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
     const unsigned char* d_in = stage_in(c, c->io_a, input, n, stride, on_device != 0);
     unsigned char* d_mask = mask;
     if (!mask_on_device) {
@@ -666,7 +686,8 @@ int gicpb_difference_run(gicpb_ctx* c, const void* input, int64_t n, int64_t str
       if ((double)tf > thr) tf = std::nextafterf(tf, -INFINITY);
       thr_next = std::nextafterf(tf, INFINITY);
     }
-    launch_difference(c->sub.view(), d_in, n, stride, thr_next, always_keep, d_mask, c->counter.get(), c->stream);
+    launch_difference(c->sub.view(), d_in, n, stride, thr_next, always_keep, d_mask, c->counter.get(), far_work(c, n),
+                      c->stream);
     unsigned long long kept = 0;
     GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
     if (!mask_on_device) GICPB_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
@@ -699,7 +720,7 @@ int gicpb_nn1(gicpb_ctx* c, const void* queries, int64_t n, int64_t stride, int 
     int* d_idx = reinterpret_cast<int*>(c->io_b.get());
     float* d_d2 = reinterpret_cast<float*>(c->io_b.get() + (size_t)n * 4);
     const float gate2 = max_dist > 0 ? round_up_to_float(max_dist * max_dist) : 0.f;
-    launch_nn1(c->tgt.view(), c->queries.get(), (int)n, T, gate2, d_idx, d_d2, nullptr, c->stream);
+    launch_nn1(c->tgt.view(), c->queries.get(), (int)n, T, gate2, d_idx, d_d2, nullptr, far_work(c, n), c->stream);
     if (idx) GICPB_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (d2) GICPB_CUDA(cudaMemcpyAsync(d2, d_d2, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -721,7 +742,7 @@ int gicpb_knn(gicpb_ctx* c, int which, int32_t* idx, float* d2) {
     normals.reserve(3 * (size_t)n);
     d_idx.reserve((size_t)n * k);
     d_d2.reserve((size_t)n * k);
-    launch_knn_covariances(g.view(), 0, n, k, normals.get(), d_idx.get(), d_d2.get(), c->stream);
+    launch_knn_covariances(g.view(), 0, n, k, normals.get(), d_idx.get(), d_d2.get(), far_work(c, n), c->stream);
     std::vector<int> hi((size_t)n * k);
     std::vector<float> hd((size_t)n * k);
     std::vector<float4> hp((size_t)n);
@@ -882,7 +903,7 @@ int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int i
         GICPB_CUDA(cudaEventRecord(c->ev0, c->stream));
         launch_nn1(c->tgt.view(), c->src.sorted_points() + c->shard_lo, n, T, gate2,
                    reinterpret_cast<int*>(c->io_b.get()), reinterpret_cast<float*>(c->io_b.get() + (size_t)n * 4), nullptr,
-                   c->stream);
+                   far_work(c, n), c->stream);
         GICPB_CUDA(cudaEventRecord(c->ev1, c->stream));
       } else {
         throw ArgError("which must be 0, 1 or 2");
@@ -898,5 +919,14 @@ int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int i
 }
 
 int64_t gicpb_launch_count(const gicpb_ctx*) { return g_launch_count; }
+
+int64_t gicpb_last_far_queries(gicpb_ctx* c) {
+  if (!c || !c->far_counter.get()) return -1;
+  DeviceGuard guard(c->device);
+  unsigned v[2] = {0, 0};
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  if (cudaMemcpy(v, c->far_counter.get(), sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int64_t)v[1];
+}
 
 }  // extern "C"

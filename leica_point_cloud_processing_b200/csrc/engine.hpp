@@ -95,7 +95,8 @@ class GridIndex {
   DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, hist_, scan_tmp_;
   DevBuf<uint32_t> occ_bits_;
   DevBuf<int> brick_slot_;
-  DevBuf<uint2> cells_, brick_range_;
+  DevBuf<uint32_t> cell_start_;
+  DevBuf<unsigned long long> sb_mask_, hb_mask_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
 };
 

@@ -161,39 +161,71 @@ __global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__
   sorted[i] = pts[vals[i]];
 }
 
-// brick heads: allocate a pool slot per occupied brick and record where the brick's points begin
-__global__ void __launch_bounds__(256) brick_heads_kernel(const uint32_t* __restrict__ keys, int n_valid,
-                                                           int* __restrict__ brick_slot, unsigned* __restrict__ scratch,
-                                                           uint32_t* __restrict__ brick_begin_tmp) {
+// flags[i] = 1 iff sorted point i is the first point of its brick
+__global__ void __launch_bounds__(256) brick_flags_kernel(const uint32_t* __restrict__ keys, int n_valid,
+                                                           uint32_t* __restrict__ flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_valid) return;
-  const uint32_t b = keys[i] >> 9;
-  if (i == 0 || (keys[i - 1] >> 9) != b) {
-    const int slot = (int)atomicAdd(&scratch[7], 1u);
-    brick_slot[b] = slot;
-    brick_begin_tmp[b] = (uint32_t)i;
-  }
+  flags[i] = (i == 0 || (keys[i - 1] >> 9) != (keys[i] >> 9)) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) tables_kernel(const uint32_t* __restrict__ keys, int n_valid,
-                                                      const int* __restrict__ brick_slot,
-                                                      const uint32_t* __restrict__ brick_begin_tmp,
-                                                      uint2* __restrict__ cells, uint2* __restrict__ brick_range,
-                                                      unsigned* __restrict__ scratch) {
+// brick heads: slot = rank of the brick among the occupied bricks (so slots ascend with the brick index); set the
+// brick's bit in its superbrick mask and the superbrick's bit in its hyperbrick mask
+__global__ void __launch_bounds__(256) brick_slots_kernel(const uint32_t* __restrict__ keys,
+                                                           const uint32_t* __restrict__ flags,
+                                                           const uint32_t* __restrict__ ranks, int n_valid, GridView g,
+                                                           int* __restrict__ brick_slot,
+                                                           unsigned long long* __restrict__ sb_mask,
+                                                           unsigned long long* __restrict__ hb_mask,
+                                                           unsigned* __restrict__ scratch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_valid) return;
-  const uint32_t k = keys[i];
-  const uint32_t b = k >> 9;
-  const bool last = (i == n_valid - 1);
-  const uint32_t kn = last ? 0xffffffffu : keys[i + 1];
-  const bool head = (i == 0) || (keys[i - 1] != k);
-  const bool tail = last || (kn != k);
-  const int slot = brick_slot[b];
-  uint2* cell = &cells[(size_t)slot * kBrickCells + (k & 511u)];
-  if (head) cell->x = (uint32_t)i;
-  if (tail) cell->y = (uint32_t)i + 1u;
-  if (last || (kn >> 9) != b) brick_range[slot] = make_uint2(brick_begin_tmp[b], (uint32_t)i + 1u);
-  if (head) atomicAdd(&scratch[8], 1u);
+  if (i == n_valid - 1) scratch[7] = ranks[i] + flags[i];  // number of occupied bricks
+  if (!flags[i]) return;
+  const int b = (int)(keys[i] >> 9);
+  brick_slot[b] = (int)ranks[i];
+  const int bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
+  const int sx = bx >> 2, sy = by >> 2, sz = bz >> 2;
+  atomicOr(&sb_mask[((size_t)sz * g.nsy + sy) * g.nsx + sx], 1ull << (((bz & 3) << 4) | ((by & 3) << 2) | (bx & 3)));
+  atomicOr(&hb_mask[((size_t)(sz >> 2) * g.nhy + (sy >> 2)) * g.nhx + (sx >> 2)],
+           1ull << (((sz & 3) << 4) | ((sy & 3) << 2) | (sx & 3)));
+}
+
+// cell_start: every entry (slot, code) = index of the first sorted point whose (slot, code) is >= it.  Point i
+// writes the entries between its predecessor's cell (exclusive) and its own cell (inclusive); the last point also
+// closes its brick and writes the terminating entry.  Each entry is written exactly once.
+__global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ flags,
+                                                          const uint32_t* __restrict__ ranks, int n_valid,
+                                                          uint32_t* __restrict__ cell_start,
+                                                          unsigned* __restrict__ scratch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool head = false;
+  if (i < n_valid) {
+    const uint32_t k = keys[i];
+    const uint32_t c = k & 511u;
+    const uint32_t slot = ranks[i] + flags[i] - 1u;
+    uint32_t* cs = cell_start + (size_t)slot * kBrickCells;
+    if (i == 0) {
+      for (uint32_t code = 0; code <= c; ++code) cs[code] = 0u;
+      head = true;
+    } else {
+      const uint32_t kp = keys[i - 1];
+      head = kp != k;
+      if (!flags[i]) {
+        for (uint32_t code = (kp & 511u) + 1u; code <= c; ++code) cs[code] = (uint32_t)i;
+      } else {
+        uint32_t* csp = cs - kBrickCells;  // the previous point lives in the previous slot
+        for (uint32_t code = (kp & 511u) + 1u; code < (uint32_t)kBrickCells; ++code) csp[code] = (uint32_t)i;
+        for (uint32_t code = 0; code <= c; ++code) cs[code] = (uint32_t)i;
+      }
+    }
+    if (i == n_valid - 1) {
+      for (uint32_t code = c + 1u; code <= (uint32_t)kBrickCells; ++code) cs[code] = (uint32_t)n_valid;
+    }
+  }
+  const unsigned heads = __popc(__ballot_sync(kFullMask, head));
+  if ((threadIdx.x & 31) == 0 && heads) atomicAdd(&scratch[8], heads);  // occupied cells (statistics only)
 }
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -341,32 +373,43 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   GICPB_LAUNCHED();
 
   // ---- brick / cell tables ----------------------------------------------------------------------------
+  g.nsx = (bd[0] + 3) / 4;
+  g.nsy = (bd[1] + 3) / 4;
+  g.nsz = (bd[2] + 3) / 4;
+  g.nhx = (g.nsx + 3) / 4;
+  g.nhy = (g.nsy + 3) / 4;
+  g.nhz = (g.nsz + 3) / 4;
+  const size_t n_sb = (size_t)g.nsx * g.nsy * g.nsz, n_hb = (size_t)g.nhx * g.nhy * g.nhz;
   brick_slot_.reserve(n_bricks);
+  sb_mask_.reserve(n_sb);
+  hb_mask_.reserve(n_hb);
   GICPB_CUDA(cudaMemsetAsync(brick_slot_.get(), 0xff, (size_t)n_bricks * sizeof(int), stream));
-  uint32_t* brick_begin_tmp = in_b ? keys_a_.get() : keys_b_.get();  // the other key buffer is free now
-  if ((int64_t)keys_a_.capacity() < n_bricks) {                      // more bricks than points: dedicated buffer
-    hist_.reserve(std::max<size_t>(hist_.capacity(), (size_t)n_bricks));
-    brick_begin_tmp = hist_.get();
-  }
-  brick_heads_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, brick_slot_.get(),
-                                                                    scratch_.get(), brick_begin_tmp);
+  GICPB_CUDA(cudaMemsetAsync(sb_mask_.get(), 0, n_sb * sizeof(unsigned long long), stream));
+  GICPB_CUDA(cudaMemsetAsync(hb_mask_.get(), 0, n_hb * sizeof(unsigned long long), stream));
+  uint32_t* flags = in_b ? keys_a_.get() : keys_b_.get();  // the other key / value buffers are free now
+  uint32_t* ranks = in_b ? vals_a_.get() : vals_b_.get();
+  brick_flags_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, flags);
+  GICPB_LAUNCHED();
+  exclusive_scan_u32(flags, ranks, n_valid, scan_tmp_.get(), stream);
+  brick_slots_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, g,
+                                                                    brick_slot_.get(), sb_mask_.get(), hb_mask_.get(),
+                                                                    scratch_.get());
   GICPB_LAUNCHED();
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
   const int64_t n_slots = hs[7];
-  cells_.reserve((size_t)n_slots * kBrickCells);
-  brick_range_.reserve(n_slots);
-  GICPB_CUDA(cudaMemsetAsync(cells_.get(), 0, (size_t)n_slots * kBrickCells * sizeof(uint2), stream));
-  tables_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, brick_slot_.get(), brick_begin_tmp,
-                                                               cells_.get(), brick_range_.get(), scratch_.get());
+  cell_start_.reserve((size_t)n_slots * kBrickCells + 1);
+  cell_start_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, cell_start_.get(),
+                                                                   scratch_.get());
   GICPB_LAUNCHED();
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
 
   g.pts = pts_sorted_.get();
   g.brick_slot = brick_slot_.get();
-  g.cells = cells_.get();
-  g.brick_range = brick_range_.get();
+  g.cell_start = cell_start_.get();
+  g.sb_mask = sb_mask_.get();
+  g.hb_mask = hb_mask_.get();
   view_ = g;
   info_.cell_size = h;
   info_.dims[0] = dims[0];

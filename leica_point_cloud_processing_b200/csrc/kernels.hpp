@@ -8,18 +8,74 @@ struct RotD {  // double 3x3, row-major: double(transformation_) top-left block 
   double m[9];
 };
 
+// Hand-over from a NEAR search kernel to its FAR instance (nn_kernels.cu, knn_cov.cu).  The near kernel writes one
+// flag byte per query (1 = this query needs the hierarchical search).  The far kernel runs `far_blocks` persistent
+// blocks; each block takes tiles of kFarTile consecutive queries from `tile_counter`, compacts the flagged ones IN
+// ORDER into shared memory and works through them with full warps - so the lanes of a far warp still hold spatial
+// neighbours (the queries are sorted by cell) and the warps of a block share cache lines.
+// flags must have room for the item count rounded up to kFarTile; tile_counter[0..1] (tile cursor, number of far
+// queries) are zeroed before each launch pair (reset_far).
+constexpr int kFarTile = 1024;  // 8 flags per thread of a 128-thread block
+struct FarWork {
+  unsigned char* flags;
+  unsigned* tile_counter;
+  int far_blocks;
+  int near_rings;  // NN-1 near instance: cell rings probed for a first candidate (1..kNearMaxRing)
+};
+
+#if defined(__CUDACC__)
+// Far-instance driver: calls body(item) for every flagged item of [0, n_items); blockDim.x must be 128.
+template <class F>
+__device__ __forceinline__ void far_for_each(const FarWork& fw, int n_items, F body) {
+  __shared__ int s_items[kFarTile];
+  __shared__ int s_warp[4];
+  __shared__ int s_tile, s_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(fw.tile_counter, 1u);
+    __syncthreads();
+    const int base = s_tile * kFarTile;
+    if (base >= n_items) break;
+    // 8 consecutive flags per thread, in item order
+    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(fw.flags + base + threadIdx.x * 8) &
+                                 0x0101010101010101ull;
+    const int cnt = __popcll(w);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int off = incl - cnt;
+    for (int k = 0; k < warp; ++k) off += s_warp[k];
+    if (threadIdx.x == 127) s_n = off + cnt;
+    for (int k = 0; k < 8; ++k)
+      if ((w >> (8 * k)) & 1ull) s_items[off++] = base + threadIdx.x * 8 + k;
+    __syncthreads();
+    const int n = s_n;
+    if (threadIdx.x == 0 && n) atomicAdd(fw.tile_counter + 1, (unsigned)n);  // statistics: queries answered here
+    for (int k = threadIdx.x; k < n; k += 128) body(s_items[k]);
+  }
+}
+#endif
+
 // ---- nn_kernels.cu ------------------------------------------------------------------------------------
+void reset_far(const FarWork& fw, int64_t n_items, cudaStream_t stream);  // before every near / far launch pair
 void launch_nn1(const GridView& g, const float4* queries, int n, const Rigid& T, float gate2, int* idx, float* d2,
-                int* pos, cudaStream_t stream);
+                int* pos, const FarWork& fw, cudaStream_t stream);
 void launch_correspondences(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, const RotD& R,
                             float gate2, const double* n_src, const double* n_tgt, double eps, int* pair_pos,
                             float* pair_d2, float4* pair_tgt, void* maha, bool maha_fp32, bool use_prev,
-                            cudaStream_t stream);
-int fitness_partial_rows(int n);
+                            const FarWork& fw, cudaStream_t stream);
+int fitness_partial_rows(int n, int far_blocks);
 void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
-                    double* partials, double* out2, cudaStream_t stream);
+                    double* partials, double* out2, const FarWork& fw, cudaStream_t stream);
 void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
-                       bool always_keep, unsigned char* mask, unsigned long long* kept, cudaStream_t stream);
+                       bool always_keep, unsigned char* mask, unsigned long long* kept, const FarWork& fw,
+                       cudaStream_t stream);
 void launch_transform(const unsigned char* in, unsigned char* out, int64_t n, int64_t stride, const Rigid& T,
                       cudaStream_t stream);
 void launch_pack_queries(const unsigned char* raw, int64_t n, int64_t stride, float4* out, cudaStream_t stream);
@@ -29,7 +85,7 @@ void launch_pack_queries(const unsigned char* raw, int64_t n, int64_t stride, fl
 // normals: 3 doubles per point, index (i - lo).  knn_idx / knn_d2 (nullable): k entries per point, row
 // (i - lo), original indices.
 void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* normals, int* knn_idx, float* knn_d2,
-                            cudaStream_t stream);
+                            const FarWork& fw, cudaStream_t stream);
 
 // ---- cost.cu ------------------------------------------------------------------------------------------
 constexpr int kCostSums = 14;  // f, g_t[3], Rsum[9], pair count

@@ -8,6 +8,12 @@
 //   fitness_kernel         Registration::getFitnessScore, reference src/GICPAlignment.cpp:103,123
 //   difference_kernel      pcl::getPointCloudDifference, reference src/Filter.cpp:176-189
 //   transform_kernel       pcl::transformPointCloud, reference src/GICPAlignment.cpp:146
+//
+// Every search kernel exists in two instances.  The NEAR instance runs one thread per query: it answers the query
+// from the cells around it (nn_near: queue the point ranges, then one flat scan) with a small register footprint,
+// and appends the few queries that need more (nothing within a cell or two, or a seed that is far off) to a device
+// work list.  The FAR instance walks that list with a persistent grid and runs the hierarchical traversal
+// (nn_far) for each entry.  Both write the same outputs, so a query is answered by exactly one of them.
 #include <climits>
 
 #include "kernels.hpp"
@@ -15,6 +21,9 @@
 namespace gicpb {
 
 namespace {
+
+constexpr int kNnThreads = 128;
+constexpr int kQueueCap = 16;  // point ranges a thread can queue before it scans (3x3 rows, some split by a brick edge)
 
 __device__ __forceinline__ NNState nn_init(float gate2) {
   NNState s;
@@ -30,62 +39,70 @@ __device__ __forceinline__ NNState nn_init(float gate2) {
   return s;
 }
 
-__global__ void __launch_bounds__(128) nn1_kernel(GridView g, const float4* __restrict__ queries, int n, Rigid T,
-                                                   float gate2, int* __restrict__ idx, float* __restrict__ d2,
-                                                   int* __restrict__ pos_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = __ldg(&queries[i]);
-  NNState s = nn_init(gate2);
-  if (finite3(p.x, p.y, p.z)) {
-    const float3 q = xform(T, p.x, p.y, p.z);
-    if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
+// Runs the search of one query in this instance.  false: the query was handed to the far instance (near only).
+template <bool kFar, bool kEarlyExit>
+__device__ __forceinline__ bool search_item(const GridView& g, float qx, float qy, float qz, NNState& s, int item,
+                                            const FarWork& fw, unsigned* qb, unsigned* qe, bool& hit) {
+  const Query q = make_query(g, qx, qy, qz);
+  if (kFar) {
+    hit = nn_far<kEarlyExit>(g, q, s);
+    return true;
   }
-  if (idx) idx[i] = s.pos >= 0 ? s.oi : -1;
-  if (d2) d2[i] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
-  if (pos_out) pos_out[i] = s.pos;
+  const int r = nn_near<kEarlyExit, kNnThreads, kQueueCap>(g, q, s, qb, qe, fw.near_rings);
+  if (r == kNear_Far) {
+    fw.flags[item] = 1;
+    return false;
+  }
+  hit = (r == kNear_Stop);
+  return true;
 }
 
-// One thread per source point of this rank's shard [lo, hi) (sorted source order).
-template <typename MT, bool kUsePrev>
-__global__ void __launch_bounds__(128)
-correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T, RotD R, float gate2,
-                      const double* __restrict__ n_src, const double* __restrict__ n_tgt, double eps,
-                      int* __restrict__ pair_pos, float* __restrict__ pair_d2, float4* __restrict__ pair_tgt,
-                      MT* __restrict__ maha) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = lo + t;
-  if (i >= hi) return;
-  const float4 p = __ldg(&src[i]);
-  const float3 q = xform(T, p.x, p.y, p.z);
-  NNState s = nn_init(gate2);
-  if (kUsePrev) {
-    const int prev = pair_pos[t];
-    if (prev >= 0) {
-      const float4 c = __ldg(&g.pts[prev]);
-      const float d = dist2(q.x, q.y, q.z, c);
-      const int oi = __float_as_int(c.w);
-      if (cand_less(d, oi, s.best, s.oi)) {
-        s.best = d;
-        s.pos = prev;
-        s.oi = oi;
-      }
-    }
-  }
-  if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
-  pair_pos[t] = s.pos;
-  pair_d2[t] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
-  if (s.pos < 0) {
-    pair_tgt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
-  const float4 c = __ldg(&g.pts[s.pos]);
-  pair_tgt[t] = make_float4(c.x, c.y, c.z, 1.0f);
+#define GICPB_NEAR_QUEUE()                                     \
+  __shared__ unsigned s_qb[kFar ? 1 : kQueueCap * kNnThreads]; \
+  __shared__ unsigned s_qe[kFar ? 1 : kQueueCap * kNnThreads]; \
+  unsigned* qb = s_qb + (kFar ? 0 : threadIdx.x);              \
+  unsigned* qe = s_qe + (kFar ? 0 : threadIdx.x)
 
-  // M = (R C1 R^T + C2)^-1 in double, C = I - (1 - eps) n n^T  (gicp.hpp: M = R*C1; temp = M*R^T; temp += C2)
+// item loop shared by all search kernels: the near grid covers the items once (one per thread, and clears the item's
+// far flag before the search may set it); the far grid works through the flagged items (kernels.hpp far_for_each)
+#define GICPB_RUN_ITEMS(n_items, body)                            \
+  if (kFar) {                                                     \
+    far_for_each(fw, (int)(n_items), body);                       \
+  } else {                                                        \
+    const int k_ = blockIdx.x * kNnThreads + threadIdx.x;         \
+    if (k_ < (int)(n_items)) {                                    \
+      fw.flags[k_] = 0;                                           \
+      body(k_);                                                   \
+    }                                                             \
+  }
+
+template <bool kFar>
+__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) nn1_kernel(GridView g, const float4* __restrict__ queries, int n, Rigid T,
+                                                          float gate2, int* __restrict__ idx, float* __restrict__ d2,
+                                                          int* __restrict__ pos_out, FarWork fw) {
+  GICPB_NEAR_QUEUE();
+  auto body = [&](int i) {
+    const float4 p = __ldg(&queries[i]);
+    NNState s = nn_init(gate2);
+    if (finite3(p.x, p.y, p.z)) {
+      const float3 q = xform(T, p.x, p.y, p.z);
+      bool hit;
+      if (finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, i, fw, qb, qe, hit)) return;
+    }
+    if (idx) idx[i] = s.pos >= 0 ? s.oi : -1;
+    if (d2) d2[i] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
+    if (pos_out) pos_out[i] = s.pos;
+  };
+  GICPB_RUN_ITEMS(n, body)
+}
+
+// M = (R C1 R^T + C2)^-1 in double, C = I - (1 - eps) n n^T  (gicp.hpp: M = R*C1; temp = M*R^T; temp += C2)
+template <typename MT>
+__device__ __forceinline__ void write_mahalanobis(const RotD& R, const double* __restrict__ ns, const double* __restrict__ nt,
+                                                  double eps, MT* __restrict__ m) {
   const double a = 1.0 - eps;
-  const double sx = n_src[3 * (size_t)t], sy = n_src[3 * (size_t)t + 1], sz = n_src[3 * (size_t)t + 2];
-  const double tx = n_tgt[3 * (size_t)s.pos], ty = n_tgt[3 * (size_t)s.pos + 1], tz = n_tgt[3 * (size_t)s.pos + 2];
+  const double sx = ns[0], sy = ns[1], sz = ns[2];
+  const double tx = nt[0], ty = nt[1], tz = nt[2];
   double C1[9] = {1.0 - a * sx * sx, -a * sx * sy, -a * sx * sz, -a * sy * sx, 1.0 - a * sy * sy, -a * sy * sz,
                   -a * sz * sx, -a * sz * sy, 1.0 - a * sz * sz};
   double RC[9];
@@ -111,11 +128,8 @@ correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi
   const double c11 = A[0] * A[8] - A[2] * A[6];
   const double c12 = A[2] * A[3] - A[0] * A[5];
   const double c20 = A[3] * A[7] - A[4] * A[6];
-  const double c21 = A[1] * A[6] - A[0] * A[7];
   const double c22 = A[0] * A[4] - A[1] * A[3];
   const double inv = 1.0 / (A[0] * c00 + A[1] * c10 + A[2] * c20);
-  (void)c10; (void)c20; (void)c21;
-  MT* m = maha + 6 * (size_t)t;
   m[0] = (MT)(c00 * inv);
   m[1] = (MT)(c01 * inv);
   m[2] = (MT)(c02 * inv);
@@ -124,22 +138,67 @@ correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi
   m[5] = (MT)(c22 * inv);
 }
 
-// fitness: partial (sum d2, count) per block -> partials[block*2 + {0,1}]
-__global__ void __launch_bounds__(128) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T,
-                                                       double max_range, double* __restrict__ partials) {
+// One item per source point of this rank's shard [lo, hi) (sorted source order); item t <-> point lo + t.
+template <typename MT, bool kUsePrev, bool kFar>
+__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8)
+correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T, RotD R, float gate2,
+                      const double* __restrict__ n_src, const double* __restrict__ n_tgt, double eps,
+                      int* __restrict__ pair_pos, float* __restrict__ pair_d2, float4* __restrict__ pair_tgt,
+                      MT* __restrict__ maha, FarWork fw) {
+  GICPB_NEAR_QUEUE();
+  auto body = [&](int t) {
+    const float4 p = __ldg(&src[lo + t]);
+    const float3 q = xform(T, p.x, p.y, p.z);
+    NNState s = nn_init(gate2);
+    if (kUsePrev) {
+      const int prev = pair_pos[t];
+      if (prev >= 0) {
+        const float4 c = __ldg(&g.pts[prev]);
+        const float d = dist2(q.x, q.y, q.z, c);
+        const int oi = __float_as_int(c.w);
+        if (cand_less(d, oi, s.best, s.oi)) {
+          s.best = d;
+          s.pos = prev;
+          s.oi = oi;
+        }
+      }
+    }
+    bool hit;
+    if (finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, t, fw, qb, qe, hit)) return;
+    pair_pos[t] = s.pos;
+    pair_d2[t] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
+    if (s.pos < 0) {
+      pair_tgt[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    const float4 c = __ldg(&g.pts[s.pos]);
+    pair_tgt[t] = make_float4(c.x, c.y, c.z, 1.0f);
+    write_mahalanobis<MT>(R, n_src + 3 * (size_t)t, n_tgt + 3 * (size_t)s.pos, eps, maha + 6 * (size_t)t);
+  };
+  GICPB_RUN_ITEMS(hi - lo, body)
+}
+
+// fitness: partial (sum d2, count) per block -> partials[(row0 + block)*2 + {0,1}]
+template <bool kFar>
+__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi,
+                                                              Rigid T, double max_range, double* __restrict__ partials,
+                                                              int row0, FarWork fw) {
+  GICPB_NEAR_QUEUE();
   __shared__ double ssum[4], scnt[4];
-  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
   double sum = 0.0, cnt = 0.0;
-  if (i < hi) {
-    const float4 p = __ldg(&src[i]);
+  auto body = [&](int t) {
+    const float4 p = __ldg(&src[lo + t]);
     const float3 q = xform(T, p.x, p.y, p.z);
     NNState s = nn_init(0.f);
-    if (finite3(q.x, q.y, q.z)) nn_search<false>(g, q.x, q.y, q.z, s);
+    bool hit;
+    if (finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, t, fw, qb, qe, hit)) return;
     if (s.pos >= 0 && (double)s.best <= max_range) {
-      sum = (double)s.best;
-      cnt = 1.0;
+      sum += (double)s.best;
+      cnt += 1.0;
     }
-  }
+  };
+  GICPB_RUN_ITEMS(hi - lo, body)
+  __syncthreads();
   sum = warp_sum(sum);
   cnt = warp_sum(cnt);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,8 +208,8 @@ __global__ void __launch_bounds__(128) fitness_kernel(GridView g, const float4* 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    partials[2 * (size_t)blockIdx.x] = (ssum[0] + ssum[1]) + (ssum[2] + ssum[3]);
-    partials[2 * (size_t)blockIdx.x + 1] = (scnt[0] + scnt[1]) + (scnt[2] + scnt[3]);
+    partials[2 * (size_t)(row0 + blockIdx.x)] = (ssum[0] + ssum[1]) + (ssum[2] + ssum[3]);
+    partials[2 * (size_t)(row0 + blockIdx.x) + 1] = (scnt[0] + scnt[1]) + (scnt[2] + scnt[3]);
   }
 }
 
@@ -174,16 +233,18 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 }
 
 // difference: mask[i] = 1 iff point i is finite and no subtract point lies within d2 <= thr (thr_next = the
-// smallest float above thr, so "d2 < thr_next" == "!(d2 > thr)").  Kept count per block -> atomicAdd.
-__global__ void __launch_bounds__(128) difference_kernel(GridView g, const unsigned char* __restrict__ raw, int64_t n,
-                                                          int64_t stride, float thr_next, int always_keep,
-                                                          unsigned char* __restrict__ mask,
-                                                          unsigned long long* __restrict__ kept) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
-  if (i < n) {
-    const float* p = reinterpret_cast<const float*>(raw + i * stride);
+// smallest float above thr, so "d2 < thr_next" == "!(d2 > thr)").  Kept count -> atomicAdd per warp.
+template <bool kFar>
+__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) difference_kernel(GridView g, const unsigned char* __restrict__ raw,
+                                                                 int64_t n, int64_t stride, float thr_next,
+                                                                 int always_keep, unsigned char* __restrict__ mask,
+                                                                 unsigned long long* __restrict__ kept, FarWork fw) {
+  GICPB_NEAR_QUEUE();
+  unsigned mine = 0;
+  auto body = [&](int i) {
+    const float* p = reinterpret_cast<const float*>(raw + (int64_t)i * stride);
     const float x = p[0], y = p[1], z = p[2];
+    bool keep = false;
     if (finite3(x, y, z)) {
       if (always_keep) {
         keep = true;  // threshold < 0: every finite point with a neighbour is kept
@@ -192,19 +253,17 @@ __global__ void __launch_bounds__(128) difference_kernel(GridView g, const unsig
         s.best = thr_next;
         s.pos = -1;
         s.oi = -1;
-        keep = !nn_search<true>(g, x, y, z, s);
+        bool hit = false;
+        if (!search_item<kFar, true>(g, x, y, z, s, i, fw, qb, qe, hit)) return;
+        keep = !hit;
       }
     }
     mask[i] = keep ? 1 : 0;
-  }
-  const unsigned b = __ballot_sync(kFullMask, keep);
-  __shared__ unsigned sc[4];
-  if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = __popc(b);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = sc[0] + sc[1] + sc[2] + sc[3];
-    if (t) atomicAdd(kept, (unsigned long long)t);
-  }
+    mine += keep ? 1u : 0u;
+  };
+  GICPB_RUN_ITEMS(n, body)
+  mine = __reduce_add_sync(kFullMask, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, (unsigned long long)mine);
 }
 
 // xyz <- T * xyz for strided points; the other bytes of each point are copied (4-byte words).  in == out is allowed:
@@ -238,58 +297,87 @@ inline unsigned nblocks(int64_t n, int threads) { return (unsigned)((n + threads
 
 }  // namespace
 
+void reset_far(const FarWork& fw, int64_t n_items, cudaStream_t stream) {
+  GICPB_CUDA(cudaMemsetAsync(fw.tile_counter, 0, 2 * sizeof(unsigned), stream));
+  const int64_t padded = (n_items + kFarTile - 1) / kFarTile * kFarTile;  // flags past the last item must read 0
+  if (padded > n_items) GICPB_CUDA(cudaMemsetAsync(fw.flags + n_items, 0, (size_t)(padded - n_items), stream));
+}
+
+namespace {
+
+}  // namespace
+
 void launch_nn1(const GridView& g, const float4* queries, int n, const Rigid& T, float gate2, int* idx, float* d2,
-                int* pos, cudaStream_t stream) {
+                int* pos, const FarWork& fw, cudaStream_t stream) {
   if (n <= 0) return;
-  nn1_kernel<<<nblocks(n, 128), 128, 0, stream>>>(g, queries, n, T, gate2, idx, d2, pos);
+  reset_far(fw, n, stream);
+  nn1_kernel<false><<<nblocks(n, kNnThreads), kNnThreads, 0, stream>>>(g, queries, n, T, gate2, idx, d2, pos, fw);
+  GICPB_LAUNCHED();
+  nn1_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, queries, n, T, gate2, idx, d2, pos, fw);
+  GICPB_LAUNCHED();
+}
+
+template <typename MT, bool kUsePrev>
+static void launch_corr_t(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, const RotD& R, float gate2,
+                          const double* n_src, const double* n_tgt, double eps, int* pair_pos, float* pair_d2,
+                          float4* pair_tgt, void* maha, const FarWork& fw, cudaStream_t stream) {
+  const unsigned nb = nblocks(hi - lo, kNnThreads);
+  correspondence_kernel<MT, kUsePrev, false><<<nb, kNnThreads, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
+                                                                             pair_pos, pair_d2, pair_tgt, (MT*)maha, fw);
+  GICPB_LAUNCHED();
+  correspondence_kernel<MT, kUsePrev, true><<<fw.far_blocks, kNnThreads, 0, stream>>>(
+      g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos, pair_d2, pair_tgt, (MT*)maha, fw);
   GICPB_LAUNCHED();
 }
 
 void launch_correspondences(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, const RotD& R,
                             float gate2, const double* n_src, const double* n_tgt, double eps, int* pair_pos,
                             float* pair_d2, float4* pair_tgt, void* maha, bool maha_fp32, bool use_prev,
-                            cudaStream_t stream) {
-  const int n = hi - lo;
-  if (n <= 0) return;
-  const unsigned nb = nblocks(n, 128);
+                            const FarWork& fw, cudaStream_t stream) {
+  if (hi - lo <= 0) return;
+  reset_far(fw, hi - lo, stream);
   if (maha_fp32) {
     if (use_prev)
-      correspondence_kernel<float, true><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos,
-                                                                 pair_d2, pair_tgt, (float*)maha);
+      launch_corr_t<float, true>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos, pair_d2, pair_tgt, maha, fw, stream);
     else
-      correspondence_kernel<float, false><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
-                                                                  pair_pos, pair_d2, pair_tgt, (float*)maha);
+      launch_corr_t<float, false>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos, pair_d2, pair_tgt, maha, fw, stream);
   } else {
     if (use_prev)
-      correspondence_kernel<double, true><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
-                                                                  pair_pos, pair_d2, pair_tgt, (double*)maha);
+      launch_corr_t<double, true>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos, pair_d2, pair_tgt, maha, fw, stream);
     else
-      correspondence_kernel<double, false><<<nb, 128, 0, stream>>>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps,
-                                                                   pair_pos, pair_d2, pair_tgt, (double*)maha);
+      launch_corr_t<double, false>(g, src, lo, hi, T, R, gate2, n_src, n_tgt, eps, pair_pos, pair_d2, pair_tgt, maha, fw, stream);
   }
-  GICPB_LAUNCHED();
 }
 
-int fitness_partial_rows(int n) { return (int)nblocks(n, 128); }
+int fitness_partial_rows(int n, int far_blocks) { return (int)nblocks(n, kNnThreads) + far_blocks; }
 
 void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
-                    double* partials, double* out2, cudaStream_t stream) {
+                    double* partials, double* out2, const FarWork& fw, cudaStream_t stream) {
   const int n = hi - lo;
   if (n <= 0) {
     GICPB_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), stream));
     return;
   }
-  const unsigned nb = nblocks(n, 128);
-  fitness_kernel<<<nb, 128, 0, stream>>>(g, src, lo, hi, T, max_range, partials);
+  reset_far(fw, n, stream);
+  const unsigned nb = nblocks(n, kNnThreads);
+  fitness_kernel<false><<<nb, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, partials, 0, fw);
   GICPB_LAUNCHED();
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb, 2, out2);
+  fitness_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, partials, (int)nb, fw);
+  GICPB_LAUNCHED();
+  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb + fw.far_blocks, 2, out2);
   GICPB_LAUNCHED();
 }
 
 void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
-                       bool always_keep, unsigned char* mask, unsigned long long* kept, cudaStream_t stream) {
+                       bool always_keep, unsigned char* mask, unsigned long long* kept, const FarWork& fw,
+                       cudaStream_t stream) {
   if (n <= 0) return;
-  difference_kernel<<<nblocks(n, 128), 128, 0, stream>>>(g, raw, n, stride, thr_next, always_keep ? 1 : 0, mask, kept);
+  reset_far(fw, n, stream);
+  difference_kernel<false><<<nblocks(n, kNnThreads), kNnThreads, 0, stream>>>(g, raw, n, stride, thr_next,
+                                                                              always_keep ? 1 : 0, mask, kept, fw);
+  GICPB_LAUNCHED();
+  difference_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, raw, n, stride, thr_next, always_keep ? 1 : 0,
+                                                                    mask, kept, fw);
   GICPB_LAUNCHED();
 }
 

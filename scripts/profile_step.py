@@ -21,5 +21,5 @@ ms_corr, _ = eng.bench_kernel(0, res["transform"], iters=3)
 ms_nn, _ = eng.bench_kernel(2, res["transform"], iters=3)
 ms_cost, _ = eng.bench_kernel(1, res["transform"], iters=3)
 mask, kept = eng.cloud_difference(synth.apply_rigid(T_star, src), tgt, 4e-4)
-print("outer", res["outer_iterations"], "evals", res["cost_evaluations"], "ms", res["ms_total"], "fit", fit,
+print("outer", res["outer_iterations"], "evals", res["cost_evaluations"], "ms", res["ms_total"], "far", res["corr_far_queries"], "fit", fit,
       "corr_ms", ms_corr, "nn_ms", ms_nn, "cost_ms", ms_cost, "kept", kept, "launches", eng.launch_count())
