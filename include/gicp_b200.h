@@ -50,9 +50,10 @@ typedef struct gicpb_params {
   int max_inner_iterations;       /* PCL max_inner_iterations_                                (20)    */
   /* engine knobs (no reference counterpart; results do not depend on them) */
   float cell_size;                /* uniform-grid cell edge in metres; <= 0 -> chosen from point density */
-  float points_per_cell;          /* density target when cell_size <= 0                       (3.0)   */
+  float points_per_cell;          /* density target when cell_size <= 0                       (6.0)   */
   int mahalanobis_fp32;           /* 0: store M as 6 doubles (default); 1: 6 floats (56 B/pair cost pass) */
   int use_previous_match;         /* 1 (default): seed each NN search with last iteration's match     */
+  int l2_persist;                 /* 1 (default): persisting-L2 window on the per-pair Mahalanobis array    */
 } gicpb_params;
 
 typedef struct gicpb_align_result {

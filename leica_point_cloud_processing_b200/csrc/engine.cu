@@ -161,6 +161,7 @@ double now_ms() {
 struct gicpb_ctx {
   int device = 0;
   int num_sms = 148;
+  size_t l2_persist_bytes = 0, l2_window_max = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   gicpb_params prm{};
@@ -246,7 +247,7 @@ void all_reduce_sum(gicpb_ctx* c, double* dev, int count) {
   check_nccl(c, c->nccl->AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream), "ncclAllReduce");
 }
 
-constexpr int kFarBlocksPerSm = 8;
+constexpr int kFarBlocksPerSm = 6;
 
 FarWork far_work(gicpb_ctx* c, int64_t n_items, int near_rings = kNearMaxRing) {
   c->far_flags.reserve((size_t)std::max<int64_t>(n_items, 1) + kFarTile);
@@ -285,9 +286,21 @@ void ensure_pair_buffers(gicpb_ctx* c) {
   c->pair_d2.reserve(ns);
   c->pair_tgt.reserve(ns);
   c->maha.reserve(6 * ns);
-  c->partials.reserve((size_t)c->num_sms * 4 * kCostSums + 2 * (size_t)fitness_partial_rows((int)ns, c->num_sms * kFarBlocksPerSm) + 64);
+  c->partials.reserve((size_t)c->num_sms * 4 * 16 + 2 * (size_t)fitness_partial_rows((int)ns, c->num_sms * kFarBlocksPerSm) + 64);
   c->ticket.reserve(4);
   c->d_sums.reserve(16);
+  // The pair arrays are re-read by every cost evaluation of an outer iteration (tens of passes over the same bytes):
+  // ask L2 to keep as much of the Mahalanobis array as its persisting carve-out holds.
+  if (c->l2_persist_bytes > 0 && c->prm.l2_persist != 0) {
+    const size_t bytes = 6 * ns * (c->prm.mahalanobis_fp32 ? sizeof(float) : sizeof(double));
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = c->maha.get();
+    attr.accessPolicyWindow.num_bytes = std::min(bytes, c->l2_window_max);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_bytes / (double)std::max<size_t>(bytes, 1));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    GICPB_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  }
 }
 
 // one correspondence pass under transform T (row-major 4x4 float)
@@ -479,9 +492,10 @@ void gicpb_default_params(gicpb_params* p) {
   p->gicp_epsilon = 1e-3;
   p->max_inner_iterations = 20;
   p->cell_size = 0.f;
-  p->points_per_cell = 3.0f;
+  p->points_per_cell = 6.0f;
   p->mahalanobis_fp32 = 0;
   p->use_previous_match = 1;
+  p->l2_persist = 1;
 }
 
 int gicpb_create(int device, gicpb_ctx** out) {
@@ -499,6 +513,12 @@ int gicpb_create(int device, gicpb_ctx** out) {
     if (prop.major < 10) throw CudaError("libgicp_b200 is built for sm_100a only; found sm_" +
                                          std::to_string(prop.major) + std::to_string(prop.minor));
     c->num_sms = prop.multiProcessorCount;
+    if (prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+      c->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
+      c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    }
+    cudaGetLastError();
     GICPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     GICPB_CUDA(cudaEventCreate(&c->ev0));
     GICPB_CUDA(cudaEventCreate(&c->ev1));
@@ -625,7 +645,7 @@ int gicpb_fitness(gicpb_ctx* c, const float transform[16], double max_range, dou
     update_shard(c);
     ensure_pair_buffers(c);
     const Rigid T = rigid_from_rowmajor(transform);
-    double* partials = c->partials.get() + (size_t)c->num_sms * 4 * kCostSums;
+    double* partials = c->partials.get() + (size_t)c->num_sms * 4 * 16;
     launch_fitness(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, max_range, partials,
                    c->d_sums.get(), far_work(c, c->shard_hi - c->shard_lo), c->stream);
     all_reduce_sum(c, c->d_sums.get(), 2);

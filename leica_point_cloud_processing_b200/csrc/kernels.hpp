@@ -29,7 +29,7 @@ template <class F>
 __device__ __forceinline__ void far_for_each(const FarWork& fw, int n_items, F body) {
   __shared__ int s_items[kFarTile];
   __shared__ int s_warp[4];
-  __shared__ int s_tile, s_n;
+  __shared__ int s_tile, s_n, s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (;;) {
     __syncthreads();
@@ -51,13 +51,23 @@ __device__ __forceinline__ void far_for_each(const FarWork& fw, int n_items, F b
     __syncthreads();
     int off = incl - cnt;
     for (int k = 0; k < warp; ++k) off += s_warp[k];
-    if (threadIdx.x == 127) s_n = off + cnt;
+    if (threadIdx.x == 127) {
+      s_n = off + cnt;
+      s_next = 0;
+    }
     for (int k = 0; k < 8; ++k)
       if ((w >> (8 * k)) & 1ull) s_items[off++] = base + threadIdx.x * 8 + k;
     __syncthreads();
     const int n = s_n;
     if (threadIdx.x == 0 && n) atomicAdd(fw.tile_counter + 1, (unsigned)n);  // statistics: queries answered here
-    for (int k = threadIdx.x; k < n; k += 128) body(s_items[k]);
+    for (;;) {  // warps take 32 consecutive items at a time
+      int k = 0;
+      if (lane == 0) k = atomicAdd(&s_next, 32);
+      k = __shfl_sync(kFullMask, k, 0);
+      if (k >= n) break;
+      if (k + lane < n) body(s_items[k + lane]);
+      __syncwarp();
+    }
   }
 }
 #endif

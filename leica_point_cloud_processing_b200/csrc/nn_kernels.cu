@@ -77,7 +77,7 @@ __device__ __forceinline__ bool search_item(const GridView& g, float qx, float q
   }
 
 template <bool kFar>
-__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) nn1_kernel(GridView g, const float4* __restrict__ queries, int n, Rigid T,
+__global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) nn1_kernel(GridView g, const float4* __restrict__ queries, int n, Rigid T,
                                                           float gate2, int* __restrict__ idx, float* __restrict__ d2,
                                                           int* __restrict__ pos_out, FarWork fw) {
   GICPB_NEAR_QUEUE();
@@ -140,7 +140,7 @@ __device__ __forceinline__ void write_mahalanobis(const RotD& R, const double* _
 
 // One item per source point of this rank's shard [lo, hi) (sorted source order); item t <-> point lo + t.
 template <typename MT, bool kUsePrev, bool kFar>
-__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8)
+__global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8)
 correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi, Rigid T, RotD R, float gate2,
                       const double* __restrict__ n_src, const double* __restrict__ n_tgt, double eps,
                       int* __restrict__ pair_pos, float* __restrict__ pair_d2, float4* __restrict__ pair_tgt,
@@ -180,7 +180,7 @@ correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi
 
 // fitness: partial (sum d2, count) per block -> partials[(row0 + block)*2 + {0,1}]
 template <bool kFar>
-__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi,
+__global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi,
                                                               Rigid T, double max_range, double* __restrict__ partials,
                                                               int row0, FarWork fw) {
   GICPB_NEAR_QUEUE();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 // difference: mask[i] = 1 iff point i is finite and no subtract point lies within d2 <= thr (thr_next = the
 // smallest float above thr, so "d2 < thr_next" == "!(d2 > thr)").  Kept count -> atomicAdd per warp.
 template <bool kFar>
-__global__ void __launch_bounds__(kNnThreads, kFar ? 8 : 8) difference_kernel(GridView g, const unsigned char* __restrict__ raw,
+__global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) difference_kernel(GridView g, const unsigned char* __restrict__ raw,
                                                                  int64_t n, int64_t stride, float thr_next,
                                                                  int always_keep, unsigned char* __restrict__ mask,
                                                                  unsigned long long* __restrict__ kept, FarWork fw) {
