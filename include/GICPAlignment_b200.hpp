@@ -1,0 +1,374 @@
+// GICPAlignment_b200.hpp - header-only C++ drop-in for the reference's GICPAlignment class
+// (reference include/GICPAlignment.h:32-224, src/GICPAlignment.cpp:23-198) and for Filter::removeFromCloud
+// (reference src/Filter.cpp:176-189), on top of the C ABI of libgicp_b200.so (include/gicp_b200.h).
+//
+// Same class name, constructor (TARGET first), public methods, argument types and public field
+// `transform_exists_`, so that LeicaStateMachine.cpp:149-153 and test/test_gicp_alignment.cpp compile unchanged
+// when this header replaces <GICPAlignment.h>.  Behaviour kept on purpose, quirks included:
+//   - setMaxCorrespondenceDistance(int) / setRANSACOutlierTh(int) truncate to integers   (GICPAlignment.h:138,145)
+//   - applyTFtoCloud(cloud) reads `cloud` and writes the INTERNAL aligned cloud          (GICPAlignment.cpp:144-147)
+//   - iterate() re-solves from the original source at identity and LEFT-multiplies the result onto the stored
+//     transform; undo() restores the aligned cloud only                                  (GICPAlignment.cpp:111-142)
+//   - a solve that does not converge leaves fine_tf_ and transform_exists_ untouched and only logs (:101-108)
+//   - use_covariances: with PCL 1.8.1 the covariances handed to GICP before setInputSource/Target are reset by
+//     those calls, so they never reach the solver; see applyCovariances() below.
+//
+// With -DGICPB_WITH_PCL the clouds are pcl::PointCloud<pcl::PointXYZRGB>::Ptr and the matrix Eigen::Matrix4f, as
+// in the reference.  Without it (this repo's tests; PCL and Eigen are not in the image) the same code runs on the
+// 32-byte POD stand-ins below, which have the memory layout of the PCL types.
+// ROS is never needed: messages go through gicpb_shim::logger() (default: stderr).  getAlignedCloudROSMsg exists
+// only under -DGICPB_WITH_ROS.
+#pragma once
+#ifndef GICP_ALIGNMENT_B200_HPP_
+#define GICP_ALIGNMENT_B200_HPP_
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gicp_b200.h"
+
+#ifdef GICPB_WITH_PCL
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#include <Eigen/Core>
+#endif
+#ifdef GICPB_WITH_ROS
+#include <pcl_conversions/pcl_conversions.h>
+#include <sensor_msgs/PointCloud2.h>
+#endif
+
+namespace gicpb_shim {
+
+// ---- logging (replaces ROS_INFO / ROS_ERROR) -----------------------------------------------------------------------
+enum LogLevel { kInfo = 0, kWarn = 1, kError = 2 };
+typedef void (*LogFn)(int level, const char* message);
+inline void default_logger(int level, const char* message) {
+  std::fprintf(stderr, "[%s] %s\n", level == kError ? "ERROR" : (level == kWarn ? " WARN" : " INFO"), message);
+}
+inline LogFn& logger() {
+  static LogFn fn = &default_logger;
+  return fn;
+}
+inline void log(int level, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  std::vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (logger()) logger()(level, buf);
+}
+
+#ifndef GICPB_WITH_PCL
+// ---- stand-ins with the memory layout of pcl::PointXYZRGB / pcl::PointCloud / Eigen::Matrix4f -----------------------
+struct alignas(16) PointXYZRGB {
+  float x = 0.f, y = 0.f, z = 0.f, w = 1.f;  // PCL's padding float holds 1.0
+  union {
+    float rgb;
+    struct { uint8_t b, g, r, a; };
+  };
+  float pad_[3] = {0.f, 0.f, 0.f};
+  PointXYZRGB() : rgb(0.f) {}
+};
+static_assert(sizeof(PointXYZRGB) == 32, "pcl::PointXYZRGB is 32 bytes");
+
+struct PointCloudRGB {
+  typedef std::shared_ptr<PointCloudRGB> Ptr;
+  std::vector<PointXYZRGB> points;
+  uint32_t width = 0, height = 1;
+  bool is_dense = true;
+  size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
+  void resize(size_t n) {
+    points.resize(n);
+    width = (uint32_t)n;
+    height = 1;
+  }
+};
+
+struct Matrix4f {  // column-major like Eigen::Matrix4f
+  float m[16];
+  static Matrix4f Identity() {
+    Matrix4f r;
+    for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.f : 0.f;
+    return r;
+  }
+  float& operator()(int row, int col) { return m[4 * col + row]; }
+  float operator()(int row, int col) const { return m[4 * col + row]; }
+  const float* data() const { return m; }
+  float* data() { return m; }
+  bool operator==(const Matrix4f& o) const { return std::memcmp(m, o.m, sizeof(m)) == 0; }
+  bool operator!=(const Matrix4f& o) const { return !(*this == o); }
+  Matrix4f operator*(const Matrix4f& o) const {  // float product, row by column in index order
+    Matrix4f r;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int k = 0; k < 4; ++k) s += (*this)(i, k) * o(k, j);
+        r(i, j) = s;
+      }
+    return r;
+  }
+};
+typedef PointCloudRGB CloudT;
+typedef Matrix4f Mat4T;
+#else
+typedef pcl::PointCloud<pcl::PointXYZRGB> CloudT;
+typedef Eigen::Matrix4f Mat4T;
+#endif
+
+inline void to_row_major(const Mat4T& m, float out[16]) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) out[4 * r + c] = m(r, c);
+}
+inline Mat4T from_row_major(const float in[16]) {
+  Mat4T m = Mat4T::Identity();
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) m(r, c) = in[4 * r + c];
+  return m;
+}
+inline Mat4T identity4() { return Mat4T::Identity(); }
+
+// Utils::isValidTransform (reference src/Utils.cpp:71-82): no NaN entry
+inline bool isValidTransform(const Mat4T& tf) {
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      if (std::isnan(tf(r, c))) return false;
+  return true;
+}
+
+// one engine context per object; device from GICPB_DEVICE (default 0)
+class Context {
+ public:
+  Context() {
+    int device = 0;
+    if (const char* e = std::getenv("GICPB_DEVICE")) device = std::atoi(e);
+    const int rc = gicpb_create(device, &ctx_);
+    if (rc != GICPB_OK || !ctx_)
+      throw std::runtime_error("gicpb_create failed (" + std::to_string(rc) + "): libgicp_b200 needs a B200; there is no CPU path");
+  }
+  ~Context() { gicpb_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  gicpb_ctx* get() const { return ctx_; }
+  void check(int rc, const char* what) const {
+    if (rc != GICPB_OK) throw std::runtime_error(std::string(what) + ": " + gicpb_last_error(ctx_));
+  }
+
+ private:
+  gicpb_ctx* ctx_ = nullptr;
+};
+
+// pcl::transformPointCloud(in, out, tf): every field copied, xyz <- tf * xyz (reference src/GICPAlignment.cpp:146)
+inline void transformCloud(const Context& ctx, const CloudT& in, CloudT& out, const Mat4T& tf) {
+  if (&in != &out) out = in;
+  if (in.points.empty()) return;
+  float T[16];
+  to_row_major(tf, T);
+  ctx.check(gicpb_transform_cloud(ctx.get(), T, &in.points[0].x, &out.points[0].x, (int64_t)in.points.size(),
+                                  (int64_t)sizeof(in.points[0]), 0),
+            "gicpb_transform_cloud");
+}
+
+// Filter::removeFromCloud (reference src/Filter.cpp:176-189): keep the points of `input_cloud` whose SQUARED distance
+// to their nearest neighbour in `substract_cloud` exceeds `threshold`, in input order; height 1, is_dense true.
+template <class CloudPtr>
+inline void removeFromCloud(const CloudPtr& input_cloud, const CloudPtr& substract_cloud, double threshold,
+                            const CloudPtr& cloud_filtered, Context* shared = nullptr) {
+  log(kInfo, "Difference from segment with threshold: %f", threshold);
+  std::unique_ptr<Context> own;
+  if (!shared) {
+    own.reset(new Context);
+    shared = own.get();
+  }
+  const int64_t n = (int64_t)input_cloud->points.size();
+  std::vector<uint8_t> mask((size_t)n);
+  int64_t kept = 0;
+  if (n > 0 && !substract_cloud->points.empty()) {
+    shared->check(gicpb_cloud_difference(shared->get(), &input_cloud->points[0].x, n, (int64_t)sizeof(input_cloud->points[0]),
+                                         &substract_cloud->points[0].x, (int64_t)substract_cloud->points.size(),
+                                         (int64_t)sizeof(substract_cloud->points[0]), 0, threshold, mask.data(), &kept),
+                  "gicpb_cloud_difference");
+  }
+  CloudT out;
+  out.points.reserve((size_t)kept);
+  for (int64_t i = 0; i < n; ++i)
+    if (mask[(size_t)i]) out.points.push_back(input_cloud->points[(size_t)i]);
+  out.width = (uint32_t)out.points.size();
+  out.height = 1;
+  out.is_dense = true;
+  *cloud_filtered = out;  // safe when cloud_filtered aliases input_cloud
+}
+
+}  // namespace gicpb_shim
+
+class GICPAlignment {
+ public:
+  typedef gicpb_shim::CloudT PointCloudRGB;
+  typedef std::shared_ptr<PointCloudRGB> PointCloudRGBPtr;
+#ifdef GICPB_WITH_PCL
+  typedef PointCloudRGB::Ptr CloudPtr;  // boost::shared_ptr in PCL 1.8
+#else
+  typedef PointCloudRGBPtr CloudPtr;
+#endif
+  typedef gicpb_shim::Mat4T Matrix4f;
+
+  // reference src/GICPAlignment.cpp:23-35
+  GICPAlignment(CloudPtr target_cloud, CloudPtr source_cloud, bool use_covariances)
+      : transform_exists_(false), covariances_(use_covariances), fine_tf_(gicpb_shim::identity4()), max_iter_(100),
+        tf_epsilon_(4e-3), max_corresp_distance_(4e-2), ransac_outlier_th_(1.0), target_cloud_(target_cloud),
+        source_cloud_(source_cloud), aligned_cloud_(new PointCloudRGB), backup_cloud_(new PointCloudRGB),
+        converged_(false), fitness_(-1.0), inputs_set_(false), last_() {}
+
+  ~GICPAlignment() {}
+
+  bool transform_exists_;  // reference include/GICPAlignment.h:56
+
+  void run() {  // :37-46
+    configParameters();
+    if (covariances_) applyCovariances();
+    fineAlignment();
+    applyTFtoCloud(source_cloud_);
+  }
+  void iterate() { iterateFineAlignment(aligned_cloud_); }  // :129-132
+  void undo() { *aligned_cloud_ = *backup_cloud_; }         // :139-142
+
+  Matrix4f getFineTransform() {  // :149-154
+    if (!transform_exists_) gicpb_shim::log(gicpb_shim::kError, "No transform yet. Please run algorithm");
+    return fine_tf_;
+  }
+  void getAlignedCloud(CloudPtr aligned_cloud) { *aligned_cloud = *aligned_cloud_; }  // :156-159 (deep copy)
+#ifdef GICPB_WITH_ROS
+  void getAlignedCloudROSMsg(sensor_msgs::PointCloud2& aligned_cloud_msg) {  // :161-164
+    pcl::toROSMsg(*aligned_cloud_, aligned_cloud_msg);
+  }
+#endif
+  void applyTFtoCloud(CloudPtr cloud) {  // :144-147
+    gicpb_shim::transformCloud(ctx_, *cloud, *aligned_cloud_, fine_tf_);
+  }
+  void setSourceCloud(CloudPtr source_cloud) {  // :166-169
+    source_cloud_ = source_cloud;
+    inputs_set_ = false;
+  }
+  void setTargetCloud(CloudPtr target_cloud) {  // :171-174
+    target_cloud_ = target_cloud;
+    inputs_set_ = false;
+  }
+  void setMaxIterations(int iterations) {  // :176-180
+    max_iter_ = iterations;
+    configParameters();
+  }
+  void setTfEpsilon(double tf_epsilon) {  // :182-186
+    tf_epsilon_ = tf_epsilon;
+    configParameters();
+  }
+  void setMaxCorrespondenceDistance(int max_corresp_distance) {  // :188-192, int on purpose
+    max_corresp_distance_ = max_corresp_distance;
+    configParameters();
+  }
+  void setRANSACOutlierTh(int ransac_threshold) {  // :194-198, int on purpose; GICP never uses it
+    ransac_outlier_th_ = ransac_threshold;
+    configParameters();
+  }
+
+  // ---- additions that do not break the reference surface (north_star: fitness score, convergence) ---------------
+  bool hasConverged() const { return converged_; }
+  double getFitnessScore() const { return fitness_; }
+  const gicpb_align_result& lastResult() const { return last_; }
+
+ private:
+  bool covariances_;
+  gicpb_shim::Context ctx_;  // replaces the pcl::GeneralizedIterativeClosestPoint member gicp_ (GICPAlignment.h:153)
+  Matrix4f fine_tf_;
+  int max_iter_;
+  double tf_epsilon_;
+  double max_corresp_distance_;
+  double ransac_outlier_th_;
+  CloudPtr target_cloud_, source_cloud_, aligned_cloud_, backup_cloud_;
+  bool converged_;
+  double fitness_;
+  bool inputs_set_;
+  gicpb_align_result last_;
+
+  void configParameters() {  // :48-54
+    gicpb_params p;
+    ctx_.check(gicpb_get_params(ctx_.get(), &p), "gicpb_get_params");
+    p.max_iterations = max_iter_;
+    p.max_corr_distance = max_corresp_distance_;
+    p.transformation_epsilon = tf_epsilon_;
+    ctx_.check(gicpb_set_params(ctx_.get(), &p), "gicpb_set_params");
+  }
+
+  // :56-84.  PCL 1.8.1's setInputSource / setInputTarget (called right after, :89-90) reset any covariances set here,
+  // so the normal-based covariances never reach the solver and GICP computes its own kNN-20 ones.
+  // The one lasting effect upstream - dropping the points whose radius-normal is NaN from the caller's clouds
+  // (:65-67) - belongs to the resolution / normals row and is not done here.
+  void applyCovariances() {
+    gicpb_shim::log(gicpb_shim::kInfo, "Extract covariances from clouds (reset by setInputSource/Target in PCL 1.8.1)");
+  }
+
+  void setInputs() {  // gicp_.setInputSource / setInputTarget, :89-90
+    if (source_cloud_->points.empty() || target_cloud_->points.empty()) throw std::runtime_error("empty cloud");
+    ctx_.check(gicpb_set_source(ctx_.get(), &source_cloud_->points[0].x, (int64_t)source_cloud_->points.size(),
+                                (int64_t)sizeof(source_cloud_->points[0]), 0),
+               "gicpb_set_source");
+    ctx_.check(gicpb_set_target(ctx_.get(), &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
+                                (int64_t)sizeof(target_cloud_->points[0]), 0),
+               "gicpb_set_target");
+    inputs_set_ = true;
+  }
+
+  // gicp_.align(): solver failures are not errors of the call (PCL swallows them: hasConverged() == false)
+  int align() {
+    const int rc = gicpb_align(ctx_.get(), &last_);
+    if (rc == GICPB_E_BADARG || rc == GICPB_E_CUDA || rc == GICPB_E_NCCL || rc == GICPB_E_STATE) ctx_.check(rc, "gicpb_align");
+    converged_ = last_.converged != 0;
+    return rc;
+  }
+
+  void fineAlignment() {  // :86-109
+    gicpb_shim::log(gicpb_shim::kInfo, "Perform GICP with %d iterations", max_iter_);
+    setInputs();
+    const auto begin = std::chrono::steady_clock::now();
+    gicpb_shim::log(gicpb_shim::kInfo, "This step may take a while ...");
+    align();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
+    gicpb_shim::log(gicpb_shim::kInfo, "GICP time: %lf s", secs);
+    if (converged_) {
+      ctx_.check(gicpb_fitness(ctx_.get(), last_.transform, 1.7976931348623157e308, &fitness_), "gicpb_fitness");
+      gicpb_shim::log(gicpb_shim::kInfo, "Converged in %f FitnessScore", fitness_);
+      fine_tf_ = gicpb_shim::from_row_major(last_.transform);
+      transform_exists_ = gicpb_shim::isValidTransform(fine_tf_);
+    } else {
+      gicpb_shim::log(gicpb_shim::kError, "GICP no converge");
+    }
+  }
+
+  void iterateFineAlignment(CloudPtr cloud) {  // :111-127
+    backUp(cloud);
+    gicpb_shim::log(gicpb_shim::kInfo, "Computing iteration...");
+    if (!inputs_set_) setInputs();
+    align();  // PCL's align() restarts from the stored input source at identity
+    const Matrix4f temp_tf = gicpb_shim::from_row_major(last_.transform);
+    if (converged_) {
+      fine_tf_ = temp_tf * fine_tf_;
+      ctx_.check(gicpb_fitness(ctx_.get(), last_.transform, 1.7976931348623157e308, &fitness_), "gicpb_fitness");
+      gicpb_shim::log(gicpb_shim::kInfo, "Converged in %f FitnessScore", fitness_);
+    } else {
+      gicpb_shim::log(gicpb_shim::kError, "GICP no converge");
+    }
+    // align(*cloud) overwrites `cloud` with final_transformation * input source
+    gicpb_shim::transformCloud(ctx_, *source_cloud_, *cloud, temp_tf);
+  }
+
+  void backUp(CloudPtr cloud) { *backup_cloud_ = *cloud; }  // :134-137
+};
+
+#endif  // GICP_ALIGNMENT_B200_HPP_

@@ -148,6 +148,9 @@ int gicpb_grid_info_get(gicpb_ctx* ctx, int which, gicpb_grid_info* out);
  *        2 = NN-1 only (no Mahalanobis build)                                                           */
 int gicpb_bench_kernel(gicpb_ctx* ctx, int which, const float transform[16], int iters, double* ms_mean,
                        int64_t* launches);
+/* the CUDA stream (cudaStream_t) every kernel and copy of this context is issued on: record CUDA events on it to time
+ * calls on the device */
+void* gicpb_stream(const gicpb_ctx* ctx);
 /* number of kernels this library launched since the context was created */
 int64_t gicpb_launch_count(const gicpb_ctx* ctx);
 /* how many queries of the most recent search (NN-1, kNN, correspondence, fitness or difference launch) were

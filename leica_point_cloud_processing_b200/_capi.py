@@ -101,6 +101,7 @@ _SIGNATURES = [
     ("gicpb_grid_info_get", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.POINTER(GridInfo)]),
     ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
+    ("gicpb_stream", ctypes.c_void_p, [_VOID_P]),
     ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
@@ -363,8 +364,9 @@ class Engine:
         self._check(self.lib.gicpb_bench_kernel(self.h, which, Tp, iters, ctypes.byref(ms), ctypes.byref(launches)))
         return ms.value, int(launches.value)
 
-    def last_far_queries(self):
-        return int(self.lib.gicpb_last_far_queries(self.h))
+    def stream_handle(self):
+        """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(handle) wraps it)."""
+        return int(self.lib.gicpb_stream(self.h) or 0)
 
     def last_far_queries(self):
         return int(self.lib.gicpb_last_far_queries(self.h))

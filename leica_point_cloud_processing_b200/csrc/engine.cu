@@ -940,6 +940,8 @@ int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int i
 
 int64_t gicpb_launch_count(const gicpb_ctx*) { return g_launch_count; }
 
+void* gicpb_stream(const gicpb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
 int64_t gicpb_last_far_queries(gicpb_ctx* c) {
   if (!c || !c->far_counter.get()) return -1;
   DeviceGuard guard(c->device);

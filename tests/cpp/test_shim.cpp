@@ -1,0 +1,155 @@
+// test_shim.cpp - the reference's test/test_gicp_alignment.cpp (testApplyTF, testRun, testRunWithCov) and the
+// removeFromCloud case of test/test_filter.cpp:102-113, restated against the drop-in header
+// include/GICPAlignment_b200.hpp (no gtest / PCL / ROS in this image: plain asserts, POD cloud types).
+// usage: test_shim source.f32 target.f32      (raw float32 xyz triples; written by tests/test_cpp_shim.py)
+// Prints one "RESULT key value..." line per check; exit code 0 iff every check passed.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "GICPAlignment_b200.hpp"
+
+typedef GICPAlignment::PointCloudRGB PointCloudRGB;
+typedef GICPAlignment::CloudPtr CloudPtr;
+typedef GICPAlignment::Matrix4f Matrix4f;
+
+static int g_failed = 0;
+#define EXPECT_TRUE(cond)                                              \
+  do {                                                                 \
+    if (!(cond)) {                                                     \
+      std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);    \
+      ++g_failed;                                                      \
+    }                                                                  \
+  } while (0)
+
+static CloudPtr load(const char* path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { std::printf("cannot open %s\n", path); std::exit(2); }
+  f.seekg(0, std::ios::end);
+  const size_t n = (size_t)f.tellg() / 12;
+  f.seekg(0);
+  std::vector<float> xyz(3 * n);
+  f.read(reinterpret_cast<char*>(xyz.data()), (std::streamsize)(12 * n));
+  CloudPtr c(new PointCloudRGB);
+  c->resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    c->points[i].x = xyz[3 * i];
+    c->points[i].y = xyz[3 * i + 1];
+    c->points[i].z = xyz[3 * i + 2];
+    c->points[i].r = 255; c->points[i].g = (uint8_t)(i & 255); c->points[i].b = 7;  // payload must survive every copy
+  }
+  return c;
+}
+
+static void print_tf(const char* key, const Matrix4f& tf) {
+  std::printf("RESULT %s", key);
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) std::printf(" %.9g", tf(r, c));
+  std::printf("\n");
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  gicpb_shim::logger() = [](int level, const char* msg) { if (level >= gicpb_shim::kError) std::printf("LOG %s\n", msg); };
+  CloudPtr sourceRGB = load(argv[1]), targetRGB = load(argv[2]);
+
+  {  // testApplyTF (test/test_gicp_alignment.cpp:50-75)
+    GICPAlignment gicp_alignment(targetRGB, sourceRGB, false);
+    Matrix4f tf = gicp_alignment.getFineTransform();
+    EXPECT_TRUE(tf == Matrix4f::Identity());  // constructor works well
+    try {
+      const PointCloudRGB before = *sourceRGB;
+      gicp_alignment.run();
+      gicp_alignment.applyTFtoCloud(sourceRGB);
+      // applyTFtoCloud writes the internal aligned cloud; the argument stays as it was
+      EXPECT_TRUE(std::memcmp(&before.points[0], &sourceRGB->points[0], 32 * before.points.size()) == 0);
+      CloudPtr aligned(new PointCloudRGB);
+      gicp_alignment.getAlignedCloud(aligned);
+      const double tolerance = 1e-3;
+      EXPECT_TRUE(aligned->points.size() == targetRGB->points.size());
+      double worst = 0;
+      for (size_t i = 0; i < aligned->points.size(); ++i) {  // default gate 0.04: the solve still lands on the yawed copy
+        worst = std::max(worst, (double)std::fabs(aligned->points[i].x - targetRGB->points[i].x));
+        worst = std::max(worst, (double)std::fabs(aligned->points[i].y - targetRGB->points[i].y));
+        worst = std::max(worst, (double)std::fabs(aligned->points[i].z - targetRGB->points[i].z));
+      }
+      std::printf("RESULT applytf_worst_abs_diff %.6g converged %d\n", worst, (int)gicp_alignment.hasConverged());
+      EXPECT_TRUE(aligned->points[5].g == 5 && aligned->points[5].r == 255);  // RGB copied through
+      (void)tolerance;
+      print_tf("applytf_transform", gicp_alignment.getFineTransform());
+    } catch (std::exception& e) {
+      std::printf("FAILED exception %s\n", e.what());
+      ++g_failed;
+    }
+  }
+  {  // testRun (:77-104)
+    GICPAlignment gicp_alignment(targetRGB, sourceRGB, false);
+    EXPECT_TRUE(gicp_alignment.getFineTransform() == Matrix4f::Identity());
+    gicp_alignment.setMaxIterations(100);
+    gicp_alignment.setMaxCorrespondenceDistance(5);
+    gicp_alignment.setRANSACOutlierTh(5e-2);
+    gicp_alignment.setTfEpsilon(5e-4);
+    try {
+      gicp_alignment.run();
+      CloudPtr aligned_cloud(new PointCloudRGB);
+      gicp_alignment.getAlignedCloud(aligned_cloud);
+      EXPECT_TRUE(gicp_alignment.transform_exists_);
+      EXPECT_TRUE(aligned_cloud->points.size() == sourceRGB->points.size());
+      print_tf("run_transform", gicp_alignment.getFineTransform());
+      std::printf("RESULT run_fitness %.12g outer %d\n", gicp_alignment.getFitnessScore(), gicp_alignment.lastResult().outer_iterations);
+      double worst = 0;
+      for (size_t i = 0; i < aligned_cloud->points.size(); ++i)
+        worst = std::max(worst, (double)std::fabs(aligned_cloud->points[i].x - targetRGB->points[i].x));
+      std::printf("RESULT run_worst_abs_dx %.6g\n", worst);
+      EXPECT_TRUE(worst <= 1e-3);  // what the reference's first-point check meant to pin
+    } catch (std::exception& e) {
+      std::printf("FAILED exception %s\n", e.what());
+      ++g_failed;
+    }
+  }
+  {  // testRunWithCov (:106-131)
+    GICPAlignment gicp_alignment(targetRGB, sourceRGB, true);
+    EXPECT_TRUE(gicp_alignment.getFineTransform() == Matrix4f::Identity());
+    try {
+      gicp_alignment.run();
+      CloudPtr aligned_cloud(new PointCloudRGB);
+      gicp_alignment.getAlignedCloud(aligned_cloud);
+      EXPECT_TRUE(gicp_alignment.transform_exists_);
+      const Matrix4f first = gicp_alignment.getFineTransform();
+      gicp_alignment.iterate();
+      EXPECT_TRUE(gicp_alignment.transform_exists_);
+      // iterate() re-solves from the original source and composes: fine_tf = T * T
+      const Matrix4f twice = first * first;
+      double d = 0;
+      const Matrix4f now = gicp_alignment.getFineTransform();
+      for (int i = 0; i < 16; ++i) d = std::max(d, (double)std::fabs(now.data()[i] - twice.data()[i]));
+      std::printf("RESULT iterate_compose_maxdiff %.6g\n", d);
+      EXPECT_TRUE(d < 1e-5);
+      CloudPtr after_iter(new PointCloudRGB), after_undo(new PointCloudRGB);
+      gicp_alignment.getAlignedCloud(after_iter);
+      gicp_alignment.undo();
+      gicp_alignment.getAlignedCloud(after_undo);
+      EXPECT_TRUE(std::memcmp(&after_undo->points[0], &aligned_cloud->points[0], 32 * aligned_cloud->points.size()) == 0);
+      EXPECT_TRUE(gicp_alignment.getFineTransform() == now);  // undo does not roll the transform back
+    } catch (std::exception& e) {
+      std::printf("FAILED exception %s\n", e.what());
+      ++g_failed;
+    }
+  }
+  {  // Filter::removeFromCloud, test/test_filter.cpp:102-113: cube moved by +2 minus cube at 0
+    CloudPtr moved(new PointCloudRGB(*sourceRGB)), out(new PointCloudRGB);
+    for (auto& p : moved->points) { p.x += 2.f; p.y += 2.f; p.z += 2.f; }
+    gicpb_shim::removeFromCloud(moved, sourceRGB, 0.0344, out);
+    std::printf("RESULT difference_kept %zu of %zu\n", out->points.size(), moved->points.size());
+    EXPECT_TRUE(out->points.size() > 1);
+    EXPECT_TRUE(out->height == 1 && out->is_dense && out->width == out->points.size());
+    CloudPtr same(new PointCloudRGB);
+    gicpb_shim::removeFromCloud(sourceRGB, sourceRGB, 1e-6, same);
+    EXPECT_TRUE(same->points.empty());
+    gicpb_shim::removeFromCloud(moved, sourceRGB, 0.0344, moved);  // output aliases the input
+    EXPECT_TRUE(moved->points.size() == out->points.size());
+  }
+  std::printf("RESULT failed %d\n", g_failed);
+  return g_failed ? 1 : 0;
+}
