@@ -30,6 +30,7 @@ struct NcclApi {
   int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
   int (*CommDestroy)(comm_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   void* handle = nullptr;
 };
@@ -47,8 +48,9 @@ NcclApi* load_nccl(const char* path, std::string& err) {
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
-  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GetErrorString) {
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather || !api.GetErrorString) {
     err = "libnccl is missing a required symbol";
     return nullptr;
   }
@@ -270,10 +272,18 @@ void ensure_covariances(gicpb_ctx* c) {
     throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points in a cloud");
   update_shard(c);
   const int ns = c->shard_hi - c->shard_lo;
-  c->n_tgt.reserve(3 * (size_t)c->tgt.n_indexed());
+  // Target covariances are needed in full on every rank, but each is a function of the target cloud alone: every rank
+  // computes one contiguous chunk of the (identically sorted) target and the chunks are all-gathered in place.
+  const int nt = c->tgt.n_indexed();
+  const int chunk = (nt + c->world - 1) / c->world;
+  const int t_lo = std::min(nt, c->rank * chunk), t_hi = std::min(nt, t_lo + chunk);
+  c->n_tgt.reserve(3 * (size_t)chunk * c->world);
   c->n_src.reserve(3 * (size_t)std::max(ns, 1));
-  const FarWork fw = far_work(c, std::max(c->tgt.n_indexed(), ns));
-  launch_knn_covariances(c->tgt.view(), 0, c->tgt.n_indexed(), k, c->n_tgt.get(), nullptr, nullptr, fw, c->stream);
+  const FarWork fw = far_work(c, std::max(chunk, ns));
+  launch_knn_covariances(c->tgt.view(), t_lo, t_hi, k, c->n_tgt.get() + 3 * (size_t)t_lo, nullptr, nullptr, fw, c->stream);
+  if (c->world > 1)
+    check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
+                                     kNcclFloat64, c->comm, c->stream), "ncclAllGather");
   launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream);
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
   c->cov_ready = true;
