@@ -83,6 +83,7 @@ struct GridView {
   const float4* pts;             // sorted points: x, y, z, w = original index (int bits)
   const int* brick_slot;         // [nbx*nby*nbz] -> table slot, -1 = empty brick; slots ascend with the brick index
   const uint32_t* cell_start;    // [n_slots*512 + 1] exclusive prefix (see the header comment); last entry = n
+  const int* pos_of;             // [n_points] original index -> position in pts (-1 for a non-finite point)
   const unsigned long long* sb_mask;  // [nsx*nsy*nsz] occupancy of the 4x4x4 bricks of a superbrick, bit (lz<<4)|(ly<<2)|lx
   const unsigned long long* hb_mask;  // [nhx*nhy*nhz] occupancy of the 4x4x4 superbricks of a hyperbrick
   float ox, oy, oz;              // origin (min corner of cell (0,0,0))

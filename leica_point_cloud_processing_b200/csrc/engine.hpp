@@ -96,6 +96,7 @@ class GridIndex {
   DevBuf<uint32_t> occ_bits_;
   DevBuf<int> brick_slot_;
   DevBuf<uint32_t> cell_start_;
+  DevBuf<int> pos_of_;
   DevBuf<unsigned long long> sb_mask_, hb_mask_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
 };

@@ -154,11 +154,20 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ pt
   vals[i] = (uint32_t)i;
 }
 
+// gather the points into sorted order and record the inverse permutation (original index -> sorted position;
+// the tail of vals, i >= n_valid, holds the non-finite points: position -1)
 __global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals,
-                                                       int64_t n, float4* __restrict__ sorted) {
+                                                       int64_t n_valid, int64_t n, float4* __restrict__ sorted,
+                                                       int* __restrict__ pos_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  sorted[i] = pts[vals[i]];
+  const uint32_t oi = vals[i];
+  if (i < n_valid) {
+    sorted[i] = pts[oi];
+    pos_of[oi] = (int)i;
+  } else {
+    pos_of[oi] = -1;
+  }
 }
 
 // flags[i] = 1 iff sorted point i is the first point of its brick
@@ -369,7 +378,9 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
                                      scan_tmp_.get(), n, key_bits, stream);
   const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
   const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
-  reorder_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, pts_sorted_.get());
+  pos_of_.reserve(n);
+  reorder_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, n, pts_sorted_.get(),
+                                                         pos_of_.get());
   GICPB_LAUNCHED();
 
   // ---- brick / cell tables ----------------------------------------------------------------------------
@@ -408,6 +419,7 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   g.pts = pts_sorted_.get();
   g.brick_slot = brick_slot_.get();
   g.cell_start = cell_start_.get();
+  g.pos_of = pos_of_.get();
   g.sb_mask = sb_mask_.get();
   g.hb_mask = hb_mask_.get();
   view_ = g;

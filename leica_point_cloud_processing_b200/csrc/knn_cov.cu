@@ -53,7 +53,7 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[9], double (&v)[9]) {
   }
 }
 
-constexpr int kKnnQueueCap = 16;
+constexpr int kKnnQueueCap = 12;
 
 template <bool kFar>
 __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
@@ -64,9 +64,8 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo
   KnnList L;
   L.pts = g.pts;
   L.lkey = reinterpret_cast<unsigned long long*>(smem) + threadIdx.x;
-  L.lpos = smem + 2 * k * kKnnThreads + threadIdx.x;
   L.k = k;
-  unsigned* qb = reinterpret_cast<unsigned*>(smem) + 3 * k * kKnnThreads + threadIdx.x;  // near instance only
+  unsigned* qb = reinterpret_cast<unsigned*>(smem) + 2 * k * kKnnThreads + threadIdx.x;  // near instance only
   unsigned* qe = qb + kKnnQueueCap * kKnnThreads;
   auto body = [&](int item) {
   const int i = lo + item;
@@ -93,7 +92,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo
   double mean0 = 0.0, mean1 = 0.0, mean2 = 0.0;
   double c00 = 0.0, c10 = 0.0, c11 = 0.0, c20 = 0.0, c21 = 0.0, c22 = 0.0;
   for (int j = 0; j < L.count; ++j) {
-    const float4 p = __ldg(&g.pts[L.pos_at(j)]);
+    const float4 p = __ldg(&g.pts[__ldg(&g.pos_of[L.oi_at(j)])]);
     mean0 += (double)p.x;
     mean1 += (double)p.y;
     mean2 += (double)p.z;
@@ -158,7 +157,7 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   const int n = hi - lo;
   if (n <= 0) return;
   reset_far(fw, n, stream);
-  const size_t heap = (size_t)3 * k * kKnnThreads * sizeof(int);
+  const size_t heap = (size_t)2 * k * kKnnThreads * sizeof(int);
   const size_t queue = (size_t)2 * kKnnQueueCap * kKnnThreads * sizeof(unsigned);
   const unsigned nb = (unsigned)((n + kKnnThreads - 1) / kKnnThreads);
   knn_cov_kernel<false><<<nb, kKnnThreads, heap + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);

@@ -11,13 +11,13 @@ namespace gicpb {
 // k-best list of one thread: a binary MAX-heap on key = (d2 bits << 32) | original index, so that the root is the
 // current k-th neighbour and "candidate beats the k-th" is one 64-bit compare with exactly the (d2, index) order
 // of the oracle (d2 >= 0, so its float bits order like unsigned integers).  Entry j of the thread lives at
-// [j * kStride] (column layout in shared memory: conflict-free).  finish() heap-sorts the list ascending.
+// [j * kStride] (column layout in shared memory: conflict-free).  finish() heap-sorts the list ascending.  Only the
+// key is kept per entry; the sorted-array position of a neighbour is GridView::pos_of[original index].
 template <int kStride>
 struct KnnVisitor {
   const float4* pts;
   float qx, qy, qz;
   unsigned long long* lkey;  // heap keys
-  int* lpos;                 // sorted-array position of each entry
   int k, count;
   unsigned long long kth_key;
   float kth_d;
@@ -31,7 +31,7 @@ struct KnnVisitor {
   GICPB_HD static unsigned long long make_key(float d, int oi) {
     return ((unsigned long long)(unsigned)f2i_bits(d) << 32) | (unsigned)oi;
   }
-  GICPB_HD void sift_down(int n, unsigned long long key, int pos) {  // place (key, pos) starting at the root of a heap of n
+  GICPB_HD void sift_down(int n, unsigned long long key) {  // place key starting at the root of a heap of n
     int j = 0;
     for (;;) {
       int c = 2 * j + 1;
@@ -43,13 +43,11 @@ struct KnnVisitor {
       }
       if (kc <= key) break;
       lkey[j * kStride] = kc;
-      lpos[j * kStride] = lpos[c * kStride];
       j = c;
     }
     lkey[j * kStride] = key;
-    lpos[j * kStride] = pos;
   }
-  GICPB_HD void insert(unsigned long long key, int pos) {
+  GICPB_HD void insert(unsigned long long key) {
     if (count < k) {  // push: sift up
       int j = count++;
       while (j > 0) {
@@ -57,21 +55,19 @@ struct KnnVisitor {
         const unsigned long long kp = lkey[p * kStride];
         if (kp >= key) break;
         lkey[j * kStride] = kp;
-        lpos[j * kStride] = lpos[p * kStride];
         j = p;
       }
       lkey[j * kStride] = key;
-      lpos[j * kStride] = pos;
       if (count < k) return;
     } else {
-      sift_down(k, key, pos);  // replace the root (the old k-th)
+      sift_down(k, key);  // replace the root (the old k-th)
     }
     kth_key = lkey[0];
     kth_d = i2f_bits((int)(kth_key >> 32));
   }
   GICPB_HD void apply(unsigned i, const float4& p) {
     const unsigned long long key = make_key(dist2(qx, qy, qz, p), f2i_bits(p.w));
-    if (key < kth_key) insert(key, (int)i);
+    if (key < kth_key) insert(key);
   }
   GICPB_HD bool point(unsigned i) {
     apply(i, ldg(&pts[i]));
@@ -91,15 +87,12 @@ struct KnnVisitor {
   GICPB_HD void finish() {  // heap sort: ascending (d2, index)
     for (int n = count - 1; n > 0; --n) {
       const unsigned long long key = lkey[n * kStride];
-      const int pos = lpos[n * kStride];
       lkey[n * kStride] = lkey[0];
-      lpos[n * kStride] = lpos[0];
-      sift_down(n, key, pos);
+      sift_down(n, key);
     }
   }
   GICPB_HD float d2_at(int j) const { return i2f_bits((int)(lkey[j * kStride] >> 32)); }
   GICPB_HD int oi_at(int j) const { return (int)(unsigned)(lkey[j * kStride] & 0xffffffffull); }
-  GICPB_HD int pos_at(int j) const { return lpos[j * kStride]; }
 };
 
 // Near part of the exact k-nearest-neighbour search of a point of the cloud itself (the query lies inside its own

@@ -21,6 +21,7 @@ struct HostIndex {
   std::vector<int> brick_slot;
   std::vector<uint32_t> cell_start;
   std::vector<unsigned long long> sb, hb;
+  std::vector<int> pos_of;
   GridView g{};
 };
 
@@ -59,9 +60,11 @@ static void build_index(const std::vector<float3>& in, float h, HostIndex& ix) {
   }
   std::stable_sort(kv.begin(), kv.end(), [](auto& a, auto& b) { return a.first < b.first; });
   ix.pts.resize(n);
+  ix.pos_of.assign(n, -1);
   for (int i = 0; i < n; ++i) {
     const float3& p = in[kv[i].second];
     ix.pts[i] = float4{p.x, p.y, p.z, i2f_bits(kv[i].second)};
+    ix.pos_of[kv[i].second] = i;
   }
   ix.brick_slot.assign((size_t)bd[0] * bd[1] * bd[2], -1);
   ix.sb.assign((size_t)g.nsx * g.nsy * g.nsz, 0ull);
@@ -99,6 +102,7 @@ static void build_index(const std::vector<float3>& in, float h, HostIndex& ix) {
   g.pts = ix.pts.data();
   g.brick_slot = ix.brick_slot.data();
   g.cell_start = ix.cell_start.data();
+  g.pos_of = ix.pos_of.data();
   g.sb_mask = ix.sb.data();
   g.hb_mask = ix.hb.data();
 }
@@ -149,21 +153,21 @@ static void check_nn(const HostIndex& ix, float qx, float qy, float qz, float ga
 }
 
 static void check_knn(const HostIndex& ix, int i, int k) {
-  std::vector<unsigned long long> lk(k); std::vector<int> lp(k);
+  std::vector<unsigned long long> lk(k);
   KnnVisitor<1> v;
-  v.pts = ix.pts.data(); v.lkey = lk.data(); v.lpos = lp.data(); v.k = k;
+  v.pts = ix.pts.data(); v.lkey = lk.data(); v.k = k;
   const float4 q = ix.pts[i];
   v.qx = q.x; v.qy = q.y; v.qz = q.z;
   unsigned qb[16], qe[16];
   const Query qq = make_query(ix.g, q.x, q.y, q.z);
-  if (mode_far_only || !knn_near<1, 16>(ix.g, qq, v, qb, qe)) { knn_far(ix.g, qq, v); ++g_knn_far; }
+  if (mode_far_only || !knn_near<1, 12>(ix.g, qq, v, qb, qe)) { knn_far(ix.g, qq, v); ++g_knn_far; }
   std::vector<std::pair<std::pair<float, int>, int>> all(ix.g.n);
   for (int j = 0; j < ix.g.n; ++j) all[j] = {{dist2(q.x, q.y, q.z, ix.pts[j]), f2i_bits(ix.pts[j].w)}, j};
   const int kk = std::min(k, ix.g.n);
   std::partial_sort(all.begin(), all.begin() + kk, all.end());
   ++g_checks;
   bool ok = v.count == kk;
-  for (int j = 0; ok && j < kk; ++j) ok = v.pos_at(j) == all[j].second && v.oi_at(j) == all[j].first.second && v.d2_at(j) == all[j].first.first;
+  for (int j = 0; ok && j < kk; ++j) ok = ix.g.pos_of[v.oi_at(j)] == all[j].second && v.oi_at(j) == all[j].first.second && v.d2_at(j) == all[j].first.first;
   if (!ok) { if (g_fail < 10) printf("kNN mismatch at sorted point %d (count %d)\n", i, v.count); ++g_fail; }
 }
 
