@@ -104,9 +104,11 @@ struct ProbeParams {
   unsigned long long word_off[kProbeLevels];
 };
 
-__global__ void __launch_bounds__(256) probe_kernel(const float4* __restrict__ pts, int64_t n, ProbeParams pp,
+// marks the occupied cells of every probe level for the points 0, sub, 2 sub, ... (a uniform subsample is enough
+// for a density estimate; the search results do not depend on the cell size)
+__global__ void __launch_bounds__(256) probe_kernel(const float4* __restrict__ pts, int64_t n, int sub, ProbeParams pp,
                                                      unsigned* __restrict__ bits) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * sub;
   if (i >= n) return;
   const float4 p = pts[i];
   if (!finite3(p.x, p.y, p.z)) return;
@@ -304,7 +306,8 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
       }
       occ_bits_.reserve(words + 16);
       GICPB_CUDA(cudaMemsetAsync(occ_bits_.get(), 0, (words + 16) * sizeof(uint32_t), stream));
-      probe_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, pp, occ_bits_.get());
+      const int sub = n >= 200000 ? 4 : 1;
+      probe_kernel<<<blocks_for((n + sub - 1) / sub, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, sub, pp, occ_bits_.get());
       GICPB_LAUNCHED();
       popcount_kernel<<<blocks_for((int64_t)words, 256), 256, 0, stream>>>(occ_bits_.get(), pp, words,
                                                                            occ_bits_.get() + words);
@@ -312,8 +315,8 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
       unsigned occ[kProbeLevels];
       GICPB_CUDA(cudaMemcpyAsync(occ, occ_bits_.get() + words, sizeof(occ), cudaMemcpyDeviceToHost, stream));
       GICPB_CUDA(cudaStreamSynchronize(stream));
-      const double N = (double)n_valid;
-      const double tau = points_per_cell > 0.f ? points_per_cell : 3.0;
+      const double N = (double)n_valid / sub;  // sampled points (the non-finite fraction is taken as uniform)
+      const double tau = (points_per_cell > 0.f ? points_per_cell : 6.0) / sub;
       int ls = -1;  // finest level whose cells are still well populated
       for (int l = 0; l < kProbeLevels; ++l)
         if (occ[l] > 0 && N / occ[l] >= 8.0) ls = l;
