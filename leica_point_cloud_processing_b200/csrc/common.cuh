@@ -496,28 +496,17 @@ constexpr int kNear_Done = 0, kNear_Stop = 1, kNear_Far = 2;
 // Near part of the exact nearest-neighbour search of (qx,qy,qz).  `s` must be initialised by the caller:
 //   ungated: {+inf, -1, INT_MAX};  gated (d2 < gate2 strictly): {gate2, -1, -1};  or a known candidate (seed).
 // kEarlyExit: stop as soon as ANY candidate beats the initial state (cloud difference) -> kNear_Stop.
-// The query's own cell, then the cell rings 1..kNearMaxRing around it, give a first candidate; the cells cut by the ball of that
-// candidate are then searched as a plain box -> kNear_Done.  When there is no candidate nearby, or the ball spans
-// too many rows, the answer is kNear_Far: the caller must run far_search (exact by itself) for this query.
+// A candidate (seed) whose ball cuts few cells is refined by searching those cells as a plain box.  Otherwise the
+// query's own cell, then the cell rings 1..rings around it, are probed for a (better) first candidate, whose ball is
+// then searched -> kNear_Done.  When nothing turns up nearby, or the ball still spans too many rows, the answer is
+// kNear_Far: the caller must run far_search (exact by itself) for this query.
 template <bool kEarlyExit, int kStride, int kCap>
 GICPB_HD int nn_near(const GridView& g, const Query& q, NNState& s, unsigned* qb, unsigned* qe, int rings = kNearMaxRing) {
   NNVisitor<kEarlyExit> v{g.pts, q.x, q.y, q.z, s};
   QueueVisitor<kStride, kCap, NNVisitor<kEarlyExit>> qv{qb, qe, 0, v};
   int result = kNear_Far;
-  do {
-    if (v.s.pos < 0) {  // no candidate yet: own cell, then the 3x3x3 block, then cell shells 2..kNearMaxRing around it
-      if (visit_run(g, q.cx, q.cx, q.cy, q.cz, v)) { result = kNear_Stop; break; }
-      bool stop = false;
-      for (int R = 1; R <= rings && v.s.pos < 0 && !stop; ++R) {
-        if (R == 1)
-          stop = visit_box(g, q, imax2(q.cx - 1, 0), imin2(q.cx + 1, g.nx - 1), imax2(q.cy - 1, 0),
-                           imin2(q.cy + 1, g.ny - 1), imax2(q.cz - 1, 0), imin2(q.cz + 1, g.nz - 1), qv);
-        else
-          stop = visit_shell(g, q, R, qv);
-        stop = stop || qv.drain();
-      }
-      if (stop) { result = kNear_Stop; break; }
-    }
+  bool probed = false;
+  for (;;) {
     if (v.s.pos >= 0) {  // a candidate bounds the ball: search the cells it cuts, if they are few
       const float rad = fadd(sqrt_up(v.s.best), g.margin);
       const int x0 = imax2(cell_of(fsub(q.x, rad), g.ox, g.inv_h), 0), x1 = imin2(cell_of(fadd(q.x, rad), g.ox, g.inv_h), g.nx - 1);
@@ -531,7 +520,24 @@ GICPB_HD int nn_near(const GridView& g, const Query& q, NNState& s, unsigned* qb
         break;
       }
     }
-  } while (false);
+    if (probed) break;  // nothing (better) nearby: the far search takes over
+    // No candidate yet, or only a poor one (a seed from a pose that has moved on): probe the query's own cell, then
+    // the 3x3x3 block, then the cell shells 2..rings around it, until something closer turns up.
+    probed = true;
+    const int start_pos = v.s.pos;
+    if (visit_run(g, q.cx, q.cx, q.cy, q.cz, v)) { result = kNear_Stop; break; }
+    bool stop = false;
+    for (int R = 1; R <= rings && v.s.pos == start_pos && !stop; ++R) {
+      if (R == 1)
+        stop = visit_box(g, q, imax2(q.cx - 1, 0), imin2(q.cx + 1, g.nx - 1), imax2(q.cy - 1, 0),
+                         imin2(q.cy + 1, g.ny - 1), imax2(q.cz - 1, 0), imin2(q.cz + 1, g.nz - 1), qv);
+      else
+        stop = visit_shell(g, q, R, qv);
+      stop = stop || qv.drain();
+    }
+    if (stop) { result = kNear_Stop; break; }
+    if (v.s.pos == start_pos) break;  // still nothing closer
+  }
   s = v.s;
   return result;
 }
