@@ -10,8 +10,9 @@
 //   - iterate() re-solves from the original source at identity and LEFT-multiplies the result onto the stored
 //     transform; undo() restores the aligned cloud only                                  (GICPAlignment.cpp:111-142)
 //   - a solve that does not converge leaves fine_tf_ and transform_exists_ untouched and only logs (:101-108)
-//   - use_covariances: with PCL 1.8.1 the covariances handed to GICP before setInputSource/Target are reset by
-//     those calls, so they never reach the solver; see applyCovariances() below.
+//   - use_covariances: the points without a finite radius-search normal are dropped from the CALLER's clouds
+//     (:63-67); the covariances themselves are reset by setInputSource/Target in PCL 1.8.1 and never reach the
+//     solver, see getCovariances() below.
 //
 // With -DGICPB_WITH_PCL the clouds are pcl::PointCloud<pcl::PointXYZRGB>::Ptr and the matrix Eigen::Matrix4f, as
 // in the reference.  Without it (this repo's tests; PCL and Eigen are not in the image) the same code runs on the
@@ -306,12 +307,37 @@ class GICPAlignment {
     ctx_.check(gicpb_set_params(ctx_.get(), &p), "gicpb_set_params");
   }
 
-  // :56-84.  PCL 1.8.1's setInputSource / setInputTarget (called right after, :89-90) reset any covariances set here,
-  // so the normal-based covariances never reach the solver and GICP computes its own kNN-20 ones.
-  // The one lasting effect upstream - dropping the points whose radius-normal is NaN from the caller's clouds
-  // (:65-67) - belongs to the resolution / normals row and is not done here.
-  void applyCovariances() {
-    gicpb_shim::log(gicpb_shim::kInfo, "Extract covariances from clouds (reset by setInputSource/Target in PCL 1.8.1)");
+  // :56-71 for one cloud.  Both resolutions are recomputed on every call, as upstream does.  The radius-search normals
+  // only decide WHICH points survive: pcl::NormalEstimation gives NaN to a point with fewer than 3 points inside the
+  // radius, removeNaNNormalsFromPointCloud + Filter::extractIndices then drop it from the CALLER's cloud (:63-67).  The
+  // covariances built from the normals (:70) are reset by setInputSource / setInputTarget in PCL 1.8.1 (:89-90,
+  // SURVEY App. A.1) and never reach the solver, so they are not built.
+  void getCovariances(CloudPtr cloud, bool is_source) {
+    setInputs();
+    double target_res = 0, source_res = 0;
+    ctx_.check(gicpb_cloud_resolution(ctx_.get(), 0, &target_res), "gicpb_cloud_resolution");
+    ctx_.check(gicpb_cloud_resolution(ctx_.get(), 1, &source_res), "gicpb_cloud_resolution");
+    const double normal_radius = (target_res + source_res) * 2.0;  // doubled
+    gicpb_shim::log(gicpb_shim::kInfo, "Computing normals with radius: %f", normal_radius);
+    std::vector<uint8_t> valid(cloud->points.size());
+    int64_t kept = 0;
+    ctx_.check(gicpb_normal_validity(ctx_.get(), is_source ? 1 : 0, normal_radius, valid.data(), &kept),
+               "gicpb_normal_validity");
+    if ((size_t)kept != cloud->points.size()) {
+      size_t w = 0;
+      for (size_t i = 0; i < cloud->points.size(); ++i)
+        if (valid[i]) cloud->points[w++] = cloud->points[i];
+      cloud->points.resize(w);
+      cloud->width = (uint32_t)w;
+      cloud->height = 1;
+      inputs_set_ = false;
+    }
+  }
+
+  void applyCovariances() {  // :73-84: source first, then target
+    gicpb_shim::log(gicpb_shim::kInfo, "Extract covariances from clouds");
+    getCovariances(source_cloud_, true);
+    getCovariances(target_cloud_, false);
   }
 
   void setInputs() {  // gicp_.setInputSource / setInputTarget, :89-90

@@ -115,6 +115,17 @@ int gicpb_difference_set_subtract(gicpb_ctx* ctx, const void* subtract, int64_t 
 int gicpb_difference_run(gicpb_ctx* ctx, const void* input, int64_t n, int64_t stride, int on_device,
                          double sqr_threshold, uint8_t* mask, int mask_on_device, int64_t* n_kept);
 
+/* ---- the use_covariances branch (GICPAlignment::getCovariances, src/GICPAlignment.cpp:56-71) ---------------------
+ * which = 0 target, 1 source (as set by gicpb_set_target / gicpb_set_source), 2 subtract.
+ * Utils::computeCloudResolution (src/Utils.cpp:145-174): mean over the finite points of the distance to the 2nd
+ * nearest neighbour (the 1st is the point itself). */
+int gicpb_cloud_resolution(gicpb_ctx* ctx, int which, double* resolution);
+/* valid[i] = 1 iff Utils::getNormals(cloud, radius) (src/Utils.cpp:27-44, pcl::NormalEstimation with a radius
+ * search) gives point i a finite normal: the point is finite and has >= 3 points (itself included) closer than
+ * `radius`.  getCovariances then drops the other points from the caller's cloud (src/GICPAlignment.cpp:63-67);
+ * valid is a host array in ORIGINAL point order. */
+int gicpb_normal_validity(gicpb_ctx* ctx, int which, double radius, uint8_t* valid, int64_t* n_valid);
+
 /* ---- test / inspection hooks (parity checks against the oracle) ------------------------------------- */
 /* exact NN-1 of `n` queries in the target: idx = ORIGINAL target index (-1: none), d2 = float32 squared
  * distance.  max_dist <= 0 -> ungated; else only neighbours with d2 < max_dist^2 (strict) are reported. */

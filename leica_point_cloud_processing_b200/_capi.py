@@ -100,6 +100,8 @@ _SIGNATURES = [
     ("gicpb_cost", ctypes.c_int, [_VOID_P, c_double_p, c_double_p, c_double_p]),
     ("gicpb_grid_info_get", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.POINTER(GridInfo)]),
     ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
+    ("gicpb_cloud_resolution", ctypes.c_int, [_VOID_P, ctypes.c_int, c_double_p]),
+    ("gicpb_normal_validity", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.c_double, c_uint8_p, c_int64_p]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
     ("gicpb_stream", ctypes.c_void_p, [_VOID_P]),
     ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
@@ -363,6 +365,21 @@ class Engine:
         launches = ctypes.c_int64()
         self._check(self.lib.gicpb_bench_kernel(self.h, which, Tp, iters, ctypes.byref(ms), ctypes.byref(launches)))
         return ms.value, int(launches.value)
+
+    def cloud_resolution(self, which):
+        """Utils::computeCloudResolution of an indexed cloud (0 target, 1 source, 2 subtract)."""
+        r = ctypes.c_double()
+        self._check(self.lib.gicpb_cloud_resolution(self.h, which, ctypes.byref(r)))
+        return r.value
+
+    def normal_validity(self, which, radius):
+        """(mask, count): which points of an indexed cloud get a finite radius-search normal (>= 3 points in the radius)."""
+        n = self.grid_info(which)["n_points"]
+        mask = np.zeros(n, np.uint8)
+        kept = ctypes.c_int64()
+        self._check(self.lib.gicpb_normal_validity(self.h, which, float(radius), mask.ctypes.data_as(c_uint8_p),
+                                                   ctypes.byref(kept)))
+        return mask, int(kept.value)
 
     def stream_handle(self):
         """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(handle) wraps it)."""

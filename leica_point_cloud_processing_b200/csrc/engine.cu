@@ -888,6 +888,42 @@ int gicpb_cost(gicpb_ctx* c, const double x[6], double* f, double g[6]) {
   });
 }
 
+int gicpb_cloud_resolution(gicpb_ctx* c, int which, double* resolution) {
+  return guarded(c, [&] {
+    if (!resolution) throw ArgError("null output");
+    GridIndex& g = pick_grid(c, which);
+    if (!g.ready()) throw StateError("cloud not set");
+    const int n = g.n_indexed();
+    const FarWork fw = far_work(c, n);
+    c->partials.reserve((size_t)c->num_sms * 4 * 16 + 2 * (size_t)fitness_partial_rows(n, fw.far_blocks) + 64);
+    c->d_sums.reserve(16);
+    launch_resolution(g.view(), c->partials.get() + (size_t)c->num_sms * 4 * 16, c->d_sums.get(), fw, c->stream);
+    GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    *resolution = c->h_sums[1] > 0 ? c->h_sums[0] / c->h_sums[1] : 0.0;
+  });
+}
+
+int gicpb_normal_validity(gicpb_ctx* c, int which, double radius, uint8_t* valid, int64_t* n_valid) {
+  return guarded(c, [&] {
+    if (!valid) throw ArgError("null output");
+    if (!(radius > 0)) throw ArgError("radius must be > 0");
+    GridIndex& g = pick_grid(c, which);
+    if (!g.ready()) throw StateError("cloud not set");
+    const int64_t total = g.n_points();
+    c->io_b.reserve((size_t)total);
+    GICPB_CUDA(cudaMemsetAsync(c->io_b.get(), 0, (size_t)total, c->stream));  // non-finite points: no normal
+    GICPB_CUDA(cudaMemsetAsync(c->counter.get(), 0, sizeof(unsigned long long), c->stream));
+    launch_radius_count(g.view(), (float)(radius * radius), 3, c->io_b.get(), c->counter.get(), far_work(c, g.n_indexed()),
+                        c->stream);
+    unsigned long long kept = 0;
+    GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaMemcpyAsync(valid, c->io_b.get(), (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_valid) *n_valid = (int64_t)kept;
+  });
+}
+
 int gicpb_grid_info_get(gicpb_ctx* c, int which, gicpb_grid_info* out) {
   return guarded(c, [&] {
     if (!out) throw ArgError("null output");

@@ -86,6 +86,11 @@ void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const 
 void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
                        bool always_keep, unsigned char* mask, unsigned long long* kept, const FarWork& fw,
                        cudaStream_t stream);
+// use_covariances branch: points with >= need neighbours inside sqrt(r2) (valid[] in ORIGINAL order; non-indexed points
+// must be pre-set to 0 by the caller), and the mean 2nd-neighbour distance sums (partials sized like the fitness ones)
+void launch_radius_count(const GridView& g, float r2, int need, unsigned char* valid, unsigned long long* kept,
+                         const FarWork& fw, cudaStream_t stream);
+void launch_resolution(const GridView& g, double* partials, double* out2, const FarWork& fw, cudaStream_t stream);
 void launch_transform(const unsigned char* in, unsigned char* out, int64_t n, int64_t stride, const Rigid& T,
                       cudaStream_t stream);
 void launch_pack_queries(const unsigned char* raw, int64_t n, int64_t stride, float4* out, cudaStream_t stream);

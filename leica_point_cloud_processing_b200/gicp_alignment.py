@@ -120,12 +120,40 @@ class GICPAlignment:
         self._engine.set_params(max_iterations=self.max_iter_, max_corr_distance=self.max_corresp_distance_,
                                 transformation_epsilon=self.tf_epsilon_)
 
+    def _get_covariances(self, which):
+        # reference :56-71 for one cloud (which: 1 source, 0 target).  Both resolutions are recomputed on every call,
+        # as upstream does; the radius-search normals only decide WHICH points survive (those with a finite normal,
+        # i.e. >= 3 points inside the radius); the covariances built from them are reset by setInputSource/Target.
+        eng = self._engine
+        eng.set_target(self.target_cloud_)
+        eng.set_source(self.source_cloud_)
+        target_res = eng.cloud_resolution(0)
+        source_res = eng.cloud_resolution(1)
+        normal_radius = (target_res + source_res) * 2.0
+        log.info("Computing normals with radius: %f", normal_radius)
+        mask, kept = eng.normal_validity(which, normal_radius)
+        cloud = self.source_cloud_ if which == 1 else self.target_cloud_
+        if kept != len(cloud):
+            keep = mask.astype(bool)
+            if hasattr(cloud, "is_cuda"):
+                import torch
+                keep = torch.from_numpy(keep).to(cloud.device)
+            cloud = cloud[keep]
+            if which == 1:
+                self.source_cloud_ = cloud
+            else:
+                self.target_cloud_ = cloud
+        self.covariance_radius_ = normal_radius
+        return kept
+
     def _apply_covariances(self):
-        # reference :56-84.  With PCL 1.8.1, setInputSource / setInputTarget (called right after, :89-90) reset any
-        # covariances set here, so the normal-based covariances never reach the solver; the only
-        # lasting effect upstream is the removal of points whose radius-normal is NaN.  That removal (a radius
-        # neighbour count on the same grid) is the "next" row 8(f)-2 and is not part of this round.
-        log.info("Extract covariances from clouds (dropped by setInputSource/Target, as in PCL 1.8.1)")
+        # reference :73-84: source first, then target.  Upstream filters the caller's clouds IN PLACE through the shared
+        # pointers; arrays cannot shrink in place, so the filtered clouds replace self.source_cloud_ / target_cloud_
+        # (the C++ drop-in mutates the caller's clouds exactly like the reference).
+        log.info("Extract covariances from clouds")
+        self._get_covariances(1)
+        self._get_covariances(0)
+        self._inputs_set = False
 
     def _fine_alignment(self):
         # reference :86-109

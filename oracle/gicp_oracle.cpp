@@ -240,6 +240,12 @@ class KdTree {
     search1(0, q, best_i, best_d);
     return best_i >= 0;
   }
+  // number of indexed points with d2 < r2 (strict, as FLANN's RadiusResultSet), counting stops at `cap`
+  int count_within(const float* q, float r2, int cap) const {
+    int found = 0;
+    if (!nodes_.empty()) count(0, q, r2, cap, found);
+    return found;
+  }
   // k nearest, sorted ascending by (d2, index); returns number found
   int knn(const float* q, int k, int* out_i, float* out_d) const {
     int found = 0;
@@ -282,6 +288,19 @@ class KdTree {
     nodes_[id].axis = axis;
     nodes_[id].split = split;
     return id;
+  }
+
+  void count(int id, const float* q, float r2, int cap, int& found) const {
+    const Node& nd = nodes_[id];
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi && found < cap; ++i)
+        if (sqdist(q, pts_ + 3 * idx_[i]) < r2) ++found;
+      return;
+    }
+    const float diff = q[nd.axis] - nd.split;
+    const int near = diff < 0.f ? nd.left : nd.right, far = diff < 0.f ? nd.right : nd.left;
+    count(near, q, r2, cap, found);
+    if (found < cap && !(diff * diff >= r2)) count(far, q, r2, cap, found);
   }
 
   void search1(int id, const float* q, int& bi, float& bd) const {
@@ -1332,12 +1351,32 @@ double orc_resolution(const float* xyz, int n) {
     int nn[2];
     float nd[2];
     if (tree.knn(xyz + 3 * i, 2, nn, nd) == 2) {
-      res += std::sqrt(nd[1]);  // sqrt(float) promoted to double, as in the reference
+      res += std::sqrt((double)nd[1]);  // the reference's unqualified sqrt() on a float: C's double sqrt(double)
       ++cnt;
     }
   }
   if (cnt) res /= (double)cnt;
   return res;
+}
+
+// Which points get a finite normal from Utils::getNormals (reference src/Utils.cpp:27-44): pcl::NormalEstimation with a
+// radius search yields NaN for a non-finite point and for a point with fewer than 3 neighbours (itself included)
+// inside the radius; GICPAlignment::getCovariances then drops exactly those points from the caller's cloud
+// (reference src/GICPAlignment.cpp:63-67).  mask[i] = 1 iff the normal of point i is finite.  Returns the count.
+int orc_normal_validity(const float* xyz, int n, double radius, unsigned char* mask) {
+  KdTree tree(xyz, n);
+  const float r2 = (float)(radius * radius);
+  int kept = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : kept) schedule(dynamic, 1024)
+#endif
+  for (int i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    const bool ok = std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && tree.count_within(p, r2, 3) >= 3;
+    mask[i] = ok ? 1 : 0;
+    kept += ok ? 1 : 0;
+  }
+  return kept;
 }
 
 }  // extern "C"

@@ -212,6 +212,15 @@ class Oracle:
                                        _p(mask, c_ubyte_p))
         return mask, int(kept)
 
+    def normal_validity(self, xyz, radius):
+        """mask[i] = 1 iff Utils::getNormals gives point i a finite normal (>= 3 points inside the radius); (mask, count)"""
+        a = _xyz(xyz)
+        mask = np.zeros(len(a), np.uint8)
+        self.lib.orc_normal_validity.restype = ctypes.c_int
+        n = self.lib.orc_normal_validity(_p(a, c_float_p), ctypes.c_int(len(a)), ctypes.c_double(radius),
+                                         _p(mask, c_ubyte_p))
+        return mask, int(n)
+
     def resolution(self, xyz):
         xyz = _xyz(xyz)
         return float(self.lib.orc_resolution(_p(xyz, c_float_p), len(xyz)))

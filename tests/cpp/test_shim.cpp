@@ -108,14 +108,26 @@ int main(int argc, char** argv) {
       ++g_failed;
     }
   }
-  {  // testRunWithCov (:106-131)
-    GICPAlignment gicp_alignment(targetRGB, sourceRGB, true);
+  {  // testRunWithCov (:106-131); use_covariances may drop points from the clouds it is given, so hand it copies
+    CloudPtr tgt_c(new PointCloudRGB(*targetRGB)), src_c(new PointCloudRGB(*sourceRGB));
+    for (int i = 0; i < 3; ++i) {  // three stray points without neighbours: no radius normal -> removed IN PLACE (:63-67)
+      src_c->points.push_back(src_c->points[i]);
+      src_c->points.back().x += 40.f + 3.f * i;
+    }
+    src_c->width = (uint32_t)src_c->points.size();
+    const size_t n_src_before = src_c->points.size();
+    GICPAlignment gicp_alignment(tgt_c, src_c, true);
     EXPECT_TRUE(gicp_alignment.getFineTransform() == Matrix4f::Identity());
     try {
       gicp_alignment.run();
       CloudPtr aligned_cloud(new PointCloudRGB);
       gicp_alignment.getAlignedCloud(aligned_cloud);
       EXPECT_TRUE(gicp_alignment.transform_exists_);
+      std::printf("RESULT cov_source_points %zu of %zu, target %zu of %zu\n", src_c->points.size(), n_src_before,
+                  tgt_c->points.size(), targetRGB->points.size());
+      EXPECT_TRUE(src_c->points.size() == n_src_before - 3);            // the caller's cloud was filtered
+      EXPECT_TRUE(tgt_c->points.size() == targetRGB->points.size());    // nothing to drop in the target
+      EXPECT_TRUE(aligned_cloud->points.size() == src_c->points.size());
       const Matrix4f first = gicp_alignment.getFineTransform();
       gicp_alignment.iterate();
       EXPECT_TRUE(gicp_alignment.transform_exists_);

@@ -346,3 +346,72 @@ def test_reference_testRunWithCov(cube_pair):
     g.undo()
     assert np.array_equal(g.getAlignedCloud(), g.backup_cloud_)
     assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)  # fine_tf_ is NOT rolled back, as upstream
+
+
+# ---- the use_covariances branch: resolution, radius-normal validity, in-place point removal --------------------
+def test_cloud_resolution_matches_oracle(engine, oracle, cube_pair):
+    """Utils::computeCloudResolution (reference src/Utils.cpp:145-174); the reference's test/test_utils.cpp:78-92 pins
+    a 0.1 lattice to 0.1 +- 0.05."""
+    src, tgt, _ = cube_pair
+    reset(engine)
+    engine.set_target(tgt)
+    engine.set_source(src)
+    for which, cloud in ((0, tgt), (1, src)):
+        r = engine.cloud_resolution(which)
+        assert abs(r - oracle.resolution(cloud)) <= 1e-12 * r
+    assert abs(engine.cloud_resolution(1) - 0.03447) < 2e-5   # the fixture fact recorded in SURVEY section 4
+    g = np.stack(np.meshgrid(*[np.arange(12) * 0.1] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    engine.set_source(g)
+    assert abs(engine.cloud_resolution(1) - 0.1) <= 1e-6
+    with_nan = np.concatenate([g, np.full((3, 3), np.nan, np.float32)])
+    engine.set_source(with_nan)
+    assert abs(engine.cloud_resolution(1) - 0.1) <= 1e-6
+
+
+@pytest.mark.parametrize("radius_factor", [0.6, 1.0, 2.0, 8.0])
+def test_normal_validity_matches_oracle(engine, oracle, radius_factor):
+    """Which points Utils::getNormals gives a finite normal (>= 3 points inside the radius), bit-exact mask."""
+    rng = np.random.default_rng(11)
+    src, tgt, _ = synth.make_pair(40_000, 40_000)
+    # isolated points and pairs (no normal), a NaN point, duplicates
+    extra = np.concatenate([rng.uniform(-3, 8, (40, 3)), [[50, 50, 50], [50, 50, 50.001]], [[np.nan, 0, 0]], src[:5]])
+    cloud = np.concatenate([src, extra.astype(np.float32)])
+    reset(engine)
+    engine.set_source(cloud)
+    radius = radius_factor * 2.0 * 2 * oracle.resolution(src)
+    mask, kept = engine.normal_validity(1, radius)
+    om, ok = oracle.normal_validity(cloud, radius)
+    assert kept == ok == int(mask.sum())
+    assert np.array_equal(mask, om)
+    assert mask[len(src) + 42] == 0 and mask[len(src) + 40] == 0   # the NaN point and the isolated pair
+    assert 0 < kept < len(cloud)
+
+
+def test_use_covariances_filters_like_the_reference(oracle):
+    """GICPAlignment(use_covariances=true).run(): the points without a finite radius normal are dropped (source first,
+    then target, each with freshly computed resolutions, reference src/GICPAlignment.cpp:56-84), then GICP runs with
+    its own kNN covariances on what is left."""
+    from leica_point_cloud_processing_b200 import GICPAlignment
+    from oracle.oracle import default_params
+    rng = np.random.default_rng(5)
+    src, tgt, _ = synth.make_pair(30_000, 30_000, angle_deg=1.0, offset_m=0.005)
+    src = np.concatenate([src, rng.uniform(5, 9, (25, 3)).astype(np.float32)])      # stray points far from the part
+    tgt = np.concatenate([tgt, rng.uniform(-9, -5, (30, 3)).astype(np.float32)])
+    g = GICPAlignment(tgt, src, True)
+    g.setMaxCorrespondenceDistance(1)
+    g.run()
+    # the same filtering, step by step, with the oracle
+    r = 2.0 * (oracle.resolution(tgt) + oracle.resolution(src))
+    ms, _ = oracle.normal_validity(src, r)
+    src_f = src[ms.astype(bool)]
+    r = 2.0 * (oracle.resolution(tgt) + oracle.resolution(src_f))
+    mt, _ = oracle.normal_validity(tgt, r)
+    tgt_f = tgt[mt.astype(bool)]
+    assert len(src_f) < len(src) and len(tgt_f) < len(tgt)
+    assert np.array_equal(g.source_cloud_, src_f) and np.array_equal(g.target_cloud_, tgt_f)
+    assert g.transform_exists_
+    ref = oracle.align(src_f, tgt_f, default_params(max_corr_distance=1.0))
+    diag = float(np.linalg.norm(tgt_f.max(0) - tgt_f.min(0)))
+    assert synth.rotation_error_rad(g.getFineTransform(), ref["T"]) <= ROT_TOL
+    assert synth.translation_error(g.getFineTransform(), ref["T"]) <= 1e-5 * diag
+    assert len(g.getAlignedCloud()) == len(src_f)
