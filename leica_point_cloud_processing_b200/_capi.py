@@ -36,6 +36,7 @@ class Params(ctypes.Structure):
         ("mahalanobis_fp32", ctypes.c_int),
         ("use_previous_match", ctypes.c_int),
         ("l2_persist", ctypes.c_int),
+        ("cost_moments", ctypes.c_int),
     ]
 
 

@@ -130,6 +130,111 @@ __global__ void __launch_bounds__(kCostThreads, 2) cost_kernel(const float4* __r
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
+
+// ---- second-order moments of the objective (one pass per OUTER iteration) ---------------------------------------------
+// The objective is a quadratic form in the 12 entries of the rigid transform: with r0_i the residual at the transform
+// T0 of this outer iteration (float, exactly as PCL evaluates it) and D = [R|t] - [R0|t0] (3x4),
+//     r_i = r0_i + D p~_i,   p~ = (x, y, z, 1)
+//     sum r^T M r   = c + sum_ak D[a][k] (B[a][k] + G[a][k])
+//     sum (M r)_a p~_k = G[a][k] = B[a][k] + sum_bl H[kl][ab] D[b][l]
+// with c = sum r0^T M r0, B[a][k] = sum p~_k (M r0)_a (12), H[kl][ab] = sum p~_k p~_l M_ab (10 x 6).  Once the 74
+// sums are on the host every f / df / fdf evaluation of the BFGS line search (OptimizationFunctorWithIndices, PCL
+// gicp.hpp) is O(1) host arithmetic: no kernel launch, no pass over the pairs, no collective.  At x = x0 the value
+// is PCL's float-transform value bit for bit; away from it the products T p are exact instead of rounded to float.
+//
+// Layout of the 74 sums: [0] c, [1 + 4a + k] B[a][k], [13] pair count, [14 + 6*kl + ab] H, kl in the order
+// 00 01 02 03 11 12 13 22 23 33, ab in the order 00 01 02 11 12 22.
+constexpr int kMomThreads = 512;          // two roles of 256 threads: both walk the same pairs
+constexpr int kMomRole = kMomThreads / 2;
+constexpr int kMomAcc = 38;               // role 0: c, B, count, H kl 0..3 (38); role 1: H kl 4..9 (36)
+constexpr int kMomRow = 80;               // doubles per partial row (74 used)
+
+template <typename MT>
+__global__ void __launch_bounds__(kMomThreads, 1) moments_kernel(const float4* __restrict__ src, int lo, int n,
+                                                                  const float4* __restrict__ pair_tgt,
+                                                                  const MT* __restrict__ maha, Rigid T0,
+                                                                  double* __restrict__ partials,
+                                                                  unsigned* __restrict__ ticket, double* __restrict__ out) {
+  double acc[kMomAcc];
+#pragma unroll
+  for (int c = 0; c < kMomAcc; ++c) acc[c] = 0.0;
+  const int role = threadIdx.x >= kMomRole ? 1 : 0;
+  const int stride = gridDim.x * kMomRole;
+  for (int t = blockIdx.x * kMomRole + (threadIdx.x & (kMomRole - 1)); t < n; t += stride) {
+    PairData<MT> d;
+    load_pair(src, pair_tgt, maha, lo, t, d);
+    if (d.q.w == 0.f) continue;  // no correspondence inside the gate
+    const double m[6] = {(double)d.m[0], (double)d.m[1], (double)d.m[2], (double)d.m[3], (double)d.m[4], (double)d.m[5]};
+    const double px = (double)d.p.x, py = (double)d.p.y, pz = (double)d.p.z;
+    if (role == 0) {
+      const float3 pp = xform(T0, d.p.x, d.p.y, d.p.z);
+      const double r0 = (double)__fsub_rn(pp.x, d.q.x);
+      const double r1 = (double)__fsub_rn(pp.y, d.q.y);
+      const double r2 = (double)__fsub_rn(pp.z, d.q.z);
+      const double t0 = m[0] * r0 + m[1] * r1 + m[2] * r2;
+      const double t1 = m[1] * r0 + m[3] * r1 + m[4] * r2;
+      const double t2 = m[2] * r0 + m[4] * r1 + m[5] * r2;
+      acc[0] += r0 * t0 + r1 * t1 + r2 * t2;
+      acc[1] += px * t0; acc[2] += py * t0; acc[3] += pz * t0; acc[4] += t0;
+      acc[5] += px * t1; acc[6] += py * t1; acc[7] += pz * t1; acc[8] += t1;
+      acc[9] += px * t2; acc[10] += py * t2; acc[11] += pz * t2; acc[12] += t2;
+      acc[13] += 1.0;
+      const double w[4] = {px * px, px * py, px * pz, px};  // kl = 00 01 02 03
+#pragma unroll
+      for (int kl = 0; kl < 4; ++kl)
+#pragma unroll
+        for (int ab = 0; ab < 6; ++ab) acc[14 + 6 * kl + ab] += w[kl] * m[ab];
+    } else {
+      const double w[5] = {py * py, py * pz, py, pz * pz, pz};  // kl = 11 12 13 22 23
+#pragma unroll
+      for (int kl = 0; kl < 5; ++kl)
+#pragma unroll
+        for (int ab = 0; ab < 6; ++ab) acc[6 * kl + ab] += w[kl] * m[ab];
+#pragma unroll
+      for (int ab = 0; ab < 6; ++ab) acc[30 + ab] += m[ab];  // kl = 33
+    }
+  }
+
+  __shared__ double sm[kMomThreads / 32][kMomAcc + 1];
+  __shared__ double red[6][kMomRow];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < kMomAcc; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0) sm[warp][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kMomAcc) {  // column of role r, accumulator j: r * 38 + j  (role 1 uses 36 of its 38)
+    const int r = threadIdx.x / kMomAcc, j = threadIdx.x % kMomAcc;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kMomRole / 32; ++w) v += sm[r * (kMomRole / 32) + w][j];
+    partials[(size_t)blockIdx.x * kMomRow + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(ticket, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last block: fixed-order sum of the per-block rows (deterministic)
+  const int c = threadIdx.x % kMomRow, grp = threadIdx.x / kMomRow;
+  if (grp < 6) {
+    double v = 0.0;
+    if (c < 2 * kMomAcc)
+      for (int b = grp; b < (int)gridDim.x; b += 6) v += __ldcg(&partials[(size_t)b * kMomRow + c]);
+    red[grp][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kMomentSums) out[threadIdx.x] = ((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x])) +
+                                                     (red[4][threadIdx.x] + red[5][threadIdx.x]);
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 }  // namespace
 
 int cost_grid_blocks(int n, int num_sms) {
@@ -146,6 +251,22 @@ void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const
   else
     cost_kernel<double><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const double*)maha, T, partials,
                                                              ticket, out14);
+  GICPB_LAUNCHED();
+}
+
+int moments_grid_blocks(int n, int num_sms) {
+  const int want = (n + kMomRole - 1) / kMomRole;
+  return std::max(1, std::min(want, num_sms));  // one 512-thread CTA per SM
+}
+
+void launch_moments(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
+                    const Rigid& T0, double* partials, unsigned* ticket, double* out74, int blocks, cudaStream_t stream) {
+  if (maha_fp32)
+    moments_kernel<float><<<blocks, kMomThreads, 0, stream>>>(src, lo, n, pair_tgt, (const float*)maha, T0, partials,
+                                                              ticket, out74);
+  else
+    moments_kernel<double><<<blocks, kMomThreads, 0, stream>>>(src, lo, n, pair_tgt, (const double*)maha, T0, partials,
+                                                               ticket, out74);
   GICPB_LAUNCHED();
 }
 

@@ -182,6 +182,11 @@ struct gicpb_ctx {
   DevBuf<double> partials;
   DevBuf<unsigned> ticket;
   DevBuf<double> d_sums;          // 16 doubles on the device (NCCL path / fitness)
+  DevBuf<double> mom_partials;    // moments pass: per-block rows
+  DevBuf<double> d_mom;           // 80 doubles on the device
+  double* h_mom = nullptr;        // pinned: the 74 moment sums of the current outer iteration (all ranks)
+  float mom_T0[16];               // the transform the moments were taken around
+  bool mom_valid = false;
   double* h_sums = nullptr;       // pinned, mapped
   double* h_sums_dev = nullptr;   // device alias of h_sums
   unsigned* h_far = nullptr;      // pinned: far-query count of the last correspondence pass
@@ -299,9 +304,11 @@ void ensure_pair_buffers(gicpb_ctx* c) {
   c->partials.reserve((size_t)c->num_sms * 4 * 16 + 2 * (size_t)fitness_partial_rows((int)ns, c->num_sms * kFarBlocksPerSm) + 64);
   c->ticket.reserve(4);
   c->d_sums.reserve(16);
+  c->mom_partials.reserve((size_t)c->num_sms * 80);
+  c->d_mom.reserve(80);
   // The pair arrays are re-read by every cost evaluation of an outer iteration (tens of passes over the same bytes):
   // ask L2 to keep as much of the Mahalanobis array as its persisting carve-out holds.
-  if (c->l2_persist_bytes > 0 && c->prm.l2_persist != 0) {
+  if (c->l2_persist_bytes > 0 && c->prm.l2_persist != 0 && c->prm.cost_moments == 0) {
     const size_t bytes = 6 * ns * (c->prm.mahalanobis_fp32 ? sizeof(float) : sizeof(double));
     cudaStreamAttrValue attr{};
     attr.accessPolicyWindow.base_ptr = c->maha.get();
@@ -332,10 +339,58 @@ void run_correspondences(gicpb_ctx* c, const float* T16, bool first) {
   GICPB_CUDA(cudaMemcpyAsync(c->h_far, c->far_counter.get() + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   c->pairs_valid = true;
   c->pairs_fp32 = fp32;
+  c->mom_valid = false;
+  if (c->prm.cost_moments != 0) {
+    // one pass over the pairs of this outer iteration: the 74 second-order moments around T (cost.cu); every cost /
+    // gradient evaluation of the inner solve is then host arithmetic.  Sharded: ONE all-reduce per outer iteration.
+    const int n = c->shard_hi - c->shard_lo;
+    launch_moments(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), fp32, T,
+                   c->mom_partials.get(), c->ticket.get(), c->d_mom.get(), moments_grid_blocks(n, c->num_sms), c->stream);
+    all_reduce_sum(c, c->d_mom.get(), kMomentSums);
+    GICPB_CUDA(cudaMemcpyAsync(c->h_mom, c->d_mom.get(), kMomentSums * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::memcpy(c->mom_T0, T16, sizeof(c->mom_T0));
+  }
+}
+
+// the 14 sums of run_cost from the moments (cost.cu header): D = [R|t](x) - [R0|t0], G = B + H D
+void cost_from_moments(gicpb_ctx* c, const double* x, double* sums) {
+  if (!c->mom_valid) {
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->mom_valid = true;
+  }
+  float T16[16];
+  state_to_transform(x, T16);
+  double D[3][4];
+  for (int a = 0; a < 3; ++a)
+    for (int k = 0; k < 4; ++k) D[a][k] = (double)T16[4 * a + k] - (double)c->mom_T0[4 * a + k];
+  const double* mo = c->h_mom;
+  static const int kl_of[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+  static const int ab_of[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+  double G[3][4];
+  double f = mo[0];
+  for (int a = 0; a < 3; ++a)
+    for (int k = 0; k < 4; ++k) {
+      double hd = 0.0;
+      for (int b = 0; b < 3; ++b)
+        for (int l = 0; l < 4; ++l) hd += mo[14 + 6 * kl_of[k][l] + ab_of[a][b]] * D[b][l];
+      const double B = mo[1 + 4 * a + k];
+      G[a][k] = B + hd;
+      f += D[a][k] * (B + G[a][k]);
+    }
+  sums[0] = f;
+  for (int a = 0; a < 3; ++a) sums[1 + a] = G[a][3];
+  for (int k = 0; k < 3; ++k)
+    for (int a = 0; a < 3; ++a) sums[4 + 3 * k + a] = G[a][k];
+  sums[13] = mo[13];
+  ++c->cost_evals;
 }
 
 // raw sums of one evaluation at x (all ranks): s[0] = sum r.Mr, s[1..3] = sum Mr, s[4..12] = sum p (Mr)^T, s[13] = m
 void run_cost(gicpb_ctx* c, const double* x, double* sums) {
+  if (c->prm.cost_moments != 0 && c->pairs_valid) {
+    cost_from_moments(c, x, sums);
+    return;
+  }
   float T16[16];
   state_to_transform(x, T16);
   const Rigid T = rigid_from_rowmajor(T16);
@@ -506,6 +561,7 @@ void gicpb_default_params(gicpb_params* p) {
   p->mahalanobis_fp32 = 0;
   p->use_previous_match = 1;
   p->l2_persist = 1;
+  p->cost_moments = 0;
 }
 
 int gicpb_create(int device, gicpb_ctx** out) {
@@ -534,6 +590,7 @@ int gicpb_create(int device, gicpb_ctx** out) {
     GICPB_CUDA(cudaEventCreate(&c->ev1));
     GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
+    GICPB_CUDA(cudaHostAlloc(&c->h_mom, 80 * sizeof(double), cudaHostAllocDefault));
     GICPB_CUDA(cudaHostAlloc(&c->h_far, 4 * sizeof(unsigned), cudaHostAllocDefault));
     c->ticket.reserve(4);
     GICPB_CUDA(cudaMemset(c->ticket.get(), 0, 4 * sizeof(unsigned)));
@@ -551,6 +608,7 @@ void gicpb_destroy(gicpb_ctx* c) {
   if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_sums) cudaFreeHost(c->h_sums);
+  if (c->h_mom) cudaFreeHost(c->h_mom);
   if (c->h_far) cudaFreeHost(c->h_far);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);

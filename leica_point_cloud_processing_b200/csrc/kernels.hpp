@@ -110,4 +110,11 @@ int cost_grid_blocks(int n, int num_sms);
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                  const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream);
 
+// second-order moments of the objective around T0 (cost.cu): 74 sums from which every later f / df evaluation of the
+// outer iteration is host arithmetic.  `partials` holds moments_grid_blocks * 80 doubles, `ticket` one zeroed uint.
+constexpr int kMomentSums = 74;
+int moments_grid_blocks(int n, int num_sms);
+void launch_moments(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
+                    const Rigid& T0, double* partials, unsigned* ticket, double* out74, int blocks, cudaStream_t stream);
+
 }  // namespace gicpb

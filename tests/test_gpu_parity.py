@@ -19,7 +19,7 @@ FIT_TOL_REL = 1e-4
 def reset(engine, **kw):
     base = dict(max_iterations=100, transformation_epsilon=4e-3, rotation_epsilon=2e-3, max_corr_distance=4e-2,
                 k_correspondences=20, gicp_epsilon=1e-3, max_inner_iterations=20, cell_size=0.0, points_per_cell=3.0,
-                mahalanobis_fp32=0, use_previous_match=1)
+                mahalanobis_fp32=0, use_previous_match=1, cost_moments=0)
     base.update(kw)
     engine.set_params(**base)
 
@@ -163,6 +163,23 @@ def test_correspondences_and_cost(engine, oracle, cube_pair):
     fo, go = oracle.cost(src, tgt, valid, oi[valid], omaha, x)
     assert abs(f - fo) <= 1e-10 * abs(fo)
     assert np.allclose(g, go, rtol=1e-9, atol=1e-12)
+    # the same evaluations from the 74 second-order moments taken around T (no pass over the pairs): identical
+    # up to the float rounding of T*p that PCL's functor carries (1e-7 relative per residual, averaged over pairs)
+    reset(engine, max_corr_distance=5.0, cost_moments=1)
+    engine.correspondences(T)
+    for xx in (x, np.array([0.01, 0.02, -0.01, 0.01, 0.02, 0.05]), np.array([0.05, -0.03, 0.02, -0.04, 0.03, 0.12])):
+        fm, gm = engine.cost(xx)
+        fo, go = oracle.cost(src, tgt, valid, oi[valid], omaha, xx)
+        assert abs(fm - fo) <= 2e-7 * abs(fo)
+        assert np.allclose(gm, go, rtol=0, atol=2e-7 * np.abs(go).max())
+    # at the expansion point itself (identity: the state reproduces the matrix exactly) the two modes agree to the last bits
+    x0 = np.zeros(6)
+    engine.correspondences(np.eye(4, dtype=np.float32))
+    fm, gm = engine.cost(x0)
+    reset(engine, max_corr_distance=5.0)
+    engine.correspondences(np.eye(4, dtype=np.float32))
+    fk, gk = engine.cost(x0)
+    assert abs(fm - fk) <= 1e-13 * abs(fk) and np.allclose(gm, gk, rtol=0, atol=1e-12 * np.abs(gk).max())
     # gated: the reference's default 0.04 m
     reset(engine, max_corr_distance=0.04)
     pairs, idx, d2, maha = engine.correspondences(np.eye(4, dtype=np.float32))
@@ -215,6 +232,27 @@ def test_align_panel_100k_matches_oracle(engine, oracle):
     fit = engine.fitness(res["transform"])
     fit_ref = oracle.fitness(src, tgt, ref["T"])
     assert abs(fit - fit_ref) <= FIT_TOL_REL * fit_ref
+
+
+def test_align_cost_moments_mode(engine, oracle):
+    """cost_moments=1 evaluates the same objective from 74 moments per outer iteration, with exact instead of
+    float-rounded T*p.  PCL's line search compares objective values that differ by less than that rounding, so the
+    BFGS path is not reproduced step for step: the result agrees with the PCL-faithful default to the slack the
+    reference's stopping rule (tf_eps 4e-3, 20 inner steps) leaves, not to the 1e-4 rad parity bar."""
+    from oracle.oracle import default_params
+    src, tgt, T_star = synth.make_pair(100_000, 100_000)
+    reset(engine, max_corr_distance=1.0, cost_moments=1)
+    engine.set_target(tgt)
+    engine.set_source(src)
+    res = engine.align()
+    ref = oracle.align(src, tgt, default_params(max_corr_distance=1.0))
+    assert res["converged"] == 1
+    assert synth.rotation_error_rad(res["transform"], ref["T"]) < 5e-4
+    assert synth.translation_error(res["transform"], ref["T"]) < 5e-4
+    # as good a registration as the faithful path: same distance to the known answer, same fitness
+    assert synth.rotation_error_rad(res["transform"], T_star) < 2e-3
+    assert synth.translation_error(res["transform"], T_star) < 5e-3
+    assert abs(engine.fitness(res["transform"]) - oracle.fitness(src, tgt, ref["T"])) <= 1e-2 * oracle.fitness(src, tgt, ref["T"])
 
 
 def test_align_fp32_mahalanobis_within_tolerance(engine, oracle, cube_pair):
