@@ -164,7 +164,8 @@ int gicpb_grid_info_get(gicpb_ctx* ctx, int which, gicpb_grid_info* out);
 /* ---- micro-benchmark hooks: run one kernel `iters` times on resident data, return mean device ms ----
  * which: 0 = correspondence pass (NN + gate + Mahalanobis) under `transform`
  *        1 = cost/gradient evaluation at x derived from `transform`
- *        2 = NN-1 only (no Mahalanobis build)                                                           */
+ *        2 = NN-1 only (no Mahalanobis build)
+ *        3 = correspondence pass with the near-probe depth of the FIRST pass of a job (initial pose)       */
 int gicpb_bench_kernel(gicpb_ctx* ctx, int which, const float transform[16], int iters, double* ms_mean,
                        int64_t* launches);
 /* the CUDA stream (cudaStream_t) every kernel and copy of this context is issued on: record CUDA events on it to time

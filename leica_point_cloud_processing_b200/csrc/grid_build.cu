@@ -306,7 +306,8 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
       }
       occ_bits_.reserve(words + 16);
       GICPB_CUDA(cudaMemsetAsync(occ_bits_.get(), 0, (words + 16) * sizeof(uint32_t), stream));
-      const int sub = n >= 200000 ? 4 : 1;
+      // ~64 k samples are plenty for a density estimate (the finest well-populated level is found from them)
+      const int sub = (int)std::max<int64_t>(1, std::min<int64_t>(64, n / 65536));
       probe_kernel<<<blocks_for((n + sub - 1) / sub, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, sub, pp, occ_bits_.get());
       GICPB_LAUNCHED();
       popcount_kernel<<<blocks_for((int64_t)words, 256), 256, 0, stream>>>(occ_bits_.get(), pp, words,

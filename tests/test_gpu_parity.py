@@ -170,8 +170,8 @@ def test_correspondences_and_cost(engine, oracle, cube_pair):
     for xx in (x, np.array([0.01, 0.02, -0.01, 0.01, 0.02, 0.05]), np.array([0.05, -0.03, 0.02, -0.04, 0.03, 0.12])):
         fm, gm = engine.cost(xx)
         fo, go = oracle.cost(src, tgt, valid, oi[valid], omaha, xx)
-        assert abs(fm - fo) <= 2e-7 * abs(fo)
-        assert np.allclose(gm, go, rtol=0, atol=2e-7 * np.abs(go).max())
+        assert abs(fm - fo) <= 2e-6 * abs(fo)
+        assert np.allclose(gm, go, rtol=0, atol=2e-6 * np.abs(go).max())
     # at the expansion point itself (identity: the state reproduces the matrix exactly) the two modes agree to the last bits
     x0 = np.zeros(6)
     engine.correspondences(np.eye(4, dtype=np.float32))
