@@ -76,7 +76,7 @@ struct alignas(16) PointXYZRGB {
     struct { uint8_t b, g, r, a; };
   };
   float pad_[3] = {0.f, 0.f, 0.f};
-  PointXYZRGB() : rgb(0.f) {}
+  PointXYZRGB() : rgb(0.f) { a = 255; }  // pcl::PointXYZRGB(): r = g = b = 0, a = 255
 };
 static_assert(sizeof(PointXYZRGB) == 32, "pcl::PointXYZRGB is 32 bytes");
 

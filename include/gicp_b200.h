@@ -134,6 +134,25 @@ int gicpb_cloud_resolution(gicpb_ctx* ctx, int which, double* resolution);
  * valid is a host array in ORIGINAL point order. */
 int gicpb_normal_validity(gicpb_ctx* ctx, int which, double radius, uint8_t* valid, int64_t* n_valid);
 
+/* ---- the callers either side of the registration path ---------------------------------------
+ * FODDetector::clusterPossibleFODs (src/FODDetector.cpp:45-58 -> pcl::EuclideanClusterExtraction::extract, called at
+ * src/LeicaStateMachine.cpp:200-205 on the difference cloud): connected components of the graph joining two points
+ * whose squared distance is < tolerance^2 (FLANN radius search, strict), kept when min_size <= size <= max_size
+ * (max_size <= 0: no upper limit, the PCL default).  labels[i] = rank of point i's cluster in PCL's output order
+ * (largest cluster first; equal sizes by lowest point index) or -1 (cluster dropped by the size filter, or a
+ * non-finite point).  The indices of one cluster, ascending, are PCL's PointIndices::indices.  labels is a host
+ * array of n; n = 0 is allowed (no clusters). */
+int gicpb_euclidean_clusters(gicpb_ctx* ctx, const void* cloud, int64_t n, int64_t stride_bytes, int on_device,
+                             double tolerance, int64_t min_size, int64_t max_size, int32_t* labels, int64_t* n_clusters);
+/* Filter::downsampleCloud (src/Filter.cpp:91-105 -> pcl::VoxelGrid<PointXYZRGB>, leaf (l, l, l), all fields
+ * downsampled): one point per occupied voxel, in ascending voxel index (PCL's output order): xyz = mean of the
+ * voxel's points (float sums), stride >= 16: data[3] = 1, stride >= 20: the rgba word at byte 16 = per-channel
+ * mean (truncated), all other bytes 0 (the last input point must extend through its rgba word).  `out` must have room for n points of the same stride (host or device like
+ * `in`).  When the voxel indices would overflow 32 bits PCL warns and passes the input through: so does this call
+ * (n_out = n, the warning is left in gicpb_last_error). */
+int gicpb_voxel_grid(gicpb_ctx* ctx, const void* in, int64_t n, int64_t stride_bytes, int on_device, double leaf_size,
+                     void* out, int64_t* n_out);
+
 /* ---- test / inspection hooks (parity checks against the oracle) ------------------------------------- */
 /* exact NN-1 of `n` queries in the target: idx = ORIGINAL target index (-1: none), d2 = float32 squared
  * distance.  max_dist <= 0 -> ungated; else only neighbours with d2 < max_dist^2 (strict) are reported. */

@@ -103,6 +103,10 @@ _SIGNATURES = [
     ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
     ("gicpb_cloud_resolution", ctypes.c_int, [_VOID_P, ctypes.c_int, c_double_p]),
     ("gicpb_normal_validity", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.c_double, c_uint8_p, c_int64_p]),
+    ("gicpb_euclidean_clusters", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                                ctypes.c_double, ctypes.c_int64, ctypes.c_int64, c_int32_p, c_int64_p]),
+    ("gicpb_voxel_grid", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
+                                        _VOID_P, c_int64_p]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
     ("gicpb_stream", ctypes.c_void_p, [_VOID_P]),
     ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
@@ -305,6 +309,38 @@ class Engine:
         self._check(self.lib.gicpb_difference_run(self.h, iptr, n, istride, idev, float(sqr_threshold), mptr, mdev,
                                                   ctypes.byref(kept)))
         return mask, int(kept.value)
+
+    # ---- the callers either side of the registration path ------------------------------------------------
+    def euclidean_clusters(self, cloud, tolerance, min_size=1, max_size=0):
+        """pcl::EuclideanClusterExtraction::extract: (labels int32 [n] in PCL's cluster order, -1 = none; n_clusters)."""
+        n = int(cloud.shape[0])
+        labels = np.full(n, -1, np.int32)
+        nc = ctypes.c_int64()
+        if n == 0:
+            self._check(self.lib.gicpb_euclidean_clusters(self.h, None, 0, 32, 0, float(tolerance), int(min_size),
+                                                          int(max_size), labels.ctypes.data_as(c_int32_p), ctypes.byref(nc)))
+            return labels, 0
+        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        self._check(self.lib.gicpb_euclidean_clusters(self.h, ptr, n, stride, dev, float(tolerance), int(min_size),
+                                                      int(max_size), labels.ctypes.data_as(c_int32_p), ctypes.byref(nc)))
+        return labels, int(nc.value)
+
+    def voxel_grid(self, cloud, leaf_size):
+        """pcl::VoxelGrid with leaf (l, l, l): the centroid points [m, same columns] in ascending voxel order."""
+        n = int(cloud.shape[0])
+        m = ctypes.c_int64()
+        if n == 0:
+            return cloud[:0]
+        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        if dev:
+            import torch
+            out = torch.zeros((n, stride // 4), dtype=torch.float32, device=keep.device)
+            optr = out.data_ptr()
+        else:
+            out = np.zeros((n, stride // 4), np.float32)
+            optr = out.ctypes.data
+        self._check(self.lib.gicpb_voxel_grid(self.h, ptr, n, stride, dev, float(leaf_size), optr, ctypes.byref(m)))
+        return out[: int(m.value)]
 
     # ---- hooks ----------------------------------------------------------------------------------------
     def nn1(self, queries, T=None, max_dist=0.0):

@@ -169,7 +169,9 @@ struct gicpb_ctx {
   gicpb_params prm{};
   std::string err;
 
-  GridIndex tgt, src, sub;
+  GridIndex tgt, src, sub, clu;
+  VoxelGrid voxel;
+  DevBuf<int> uf_parent, uf_root;
   bool cov_ready = false;
   int shard_lo = 0, shard_hi = 0;
   DevBuf<double> n_tgt, n_src;
@@ -980,6 +982,101 @@ int gicpb_normal_validity(gicpb_ctx* c, int which, double radius, uint8_t* valid
     GICPB_CUDA(cudaMemcpyAsync(valid, c->io_b.get(), (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
     if (n_valid) *n_valid = (int64_t)kept;
+  });
+}
+
+int gicpb_euclidean_clusters(gicpb_ctx* c, const void* cloud, int64_t n, int64_t stride, int on_device, double tolerance,
+                             int64_t min_size, int64_t max_size, int32_t* labels, int64_t* n_clusters) {
+  return guarded(c, [&] {
+    if (!labels && n > 0) throw ArgError("null labels");
+    if (n_clusters) *n_clusters = 0;
+    if (n == 0) return;  // pcl::EuclideanClusterExtraction on an empty cloud: no clusters
+    check_cloud_args(cloud, n, stride);
+    if (!(tolerance > 0)) throw ArgError("cluster tolerance must be > 0");
+    if (max_size <= 0) max_size = INT_MAX;  // PCL default max_pts_per_cluster_
+    // cells of the tolerance: the ball of a query cuts at most 3 x 3 x 3 of them
+    bool any_finite = true;
+    try {
+      c->clu.build(cloud, n, stride, on_device != 0, (float)tolerance, c->prm.points_per_cell, c->stream);
+    } catch (const ArgError& e) {
+      if (std::string(e.what()) != "cloud has no finite point") throw;
+      any_finite = false;
+    }
+    std::vector<int> root((size_t)n, -1);
+    if (any_finite) {
+      const GridView& g = c->clu.view();
+      c->uf_parent.reserve((size_t)g.n);
+      c->uf_root.reserve((size_t)n);
+      GICPB_CUDA(cudaMemsetAsync(c->uf_root.get(), 0xff, (size_t)n * sizeof(int), c->stream));
+      const float r2 = (float)(tolerance * tolerance);  // KdTreeFLANN::radiusSearch: float(radius * radius), d2 < r2
+      launch_cluster_unions(g, r2, c->uf_parent.get(), c->uf_root.get(), far_work(c, g.n), c->stream);
+      GICPB_CUDA(cudaMemcpyAsync(root.data(), c->uf_root.get(), (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // sizes, size filter, and PCL's output order: clusters by size, largest first (extract() sorts them; equal sizes
+    // keep the order in which PCL's seed loop discovers them = by their lowest point index)
+    std::vector<int> size((size_t)n, 0), first((size_t)n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+      const int r = root[(size_t)i];
+      if (r < 0) continue;
+      if (size[(size_t)r]++ == 0) first[(size_t)r] = (int)i;
+    }
+    std::vector<int> keep;
+    for (int64_t r = 0; r < n; ++r)
+      if (size[(size_t)r] > 0 && size[(size_t)r] >= min_size && size[(size_t)r] <= max_size) keep.push_back((int)r);
+    std::stable_sort(keep.begin(), keep.end(), [&](int a, int b) {
+      if (size[(size_t)a] != size[(size_t)b]) return size[(size_t)a] > size[(size_t)b];
+      return first[(size_t)a] < first[(size_t)b];
+    });
+    std::vector<int> rank((size_t)n, -1);
+    for (size_t k = 0; k < keep.size(); ++k) rank[(size_t)keep[k]] = (int)k;
+    for (int64_t i = 0; i < n; ++i) {
+      const int r = root[(size_t)i];
+      labels[i] = r >= 0 ? rank[(size_t)r] : -1;
+    }
+    if (n_clusters) *n_clusters = (int64_t)keep.size();
+  });
+}
+
+int gicpb_voxel_grid(gicpb_ctx* c, const void* in, int64_t n, int64_t stride, int on_device, double leaf_size, void* out,
+                     int64_t* n_out) {
+  return guarded(c, [&] {
+    if (!n_out) throw ArgError("null n_out");
+    *n_out = 0;
+    if (n == 0) return;
+    if (!out) throw ArgError("null output");
+    check_cloud_args(in, n, stride);
+    if (!(leaf_size > 0)) throw ArgError("leaf size must be > 0");
+    // the last point must reach through its z, and through its rgba word when the stride holds one
+    const size_t full = (size_t)n * stride, bytes = (size_t)(n - 1) * stride + (stride >= 20 ? 20 : 12);
+    const unsigned char* d_in = static_cast<const unsigned char*>(in);
+    unsigned char* d_out = static_cast<unsigned char*>(out);
+    if (!on_device) {
+      c->io_a.reserve(full);
+      c->io_b.reserve(full);
+      GICPB_CUDA(cudaMemsetAsync(c->io_a.get() + bytes, 0, full - bytes, c->stream));
+      GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), in, bytes, cudaMemcpyHostToDevice, c->stream));
+      d_in = c->io_a.get();
+      d_out = c->io_b.get();
+    }
+    bool overflow = false;
+    const int64_t m = c->voxel.run(d_in, n, stride, (float)leaf_size, d_out, c->stream, &overflow);
+    if (overflow) {  // pcl::VoxelGrid: warns and passes the input through unchanged
+      c->err = "Leaf size is too small for the input dataset. Integer indices would overflow.";
+      if (on_device) {
+        if (out != in) GICPB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, c->stream));
+      } else if (out != in) {
+        std::memmove(out, in, bytes);
+      }
+      GICPB_CUDA(cudaStreamSynchronize(c->stream));
+      *n_out = n;
+      return;
+    }
+    if (!on_device && m > 0)
+      GICPB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)(m - 1) * stride + std::min<size_t>((size_t)stride, 20), cudaMemcpyDeviceToHost,
+                                 c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    *n_out = m;
   });
 }
 

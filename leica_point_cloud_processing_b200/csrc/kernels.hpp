@@ -110,6 +110,25 @@ int cost_grid_blocks(int n, int num_sms);
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                  const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream);
 
+// ---- segment.cu -----------------------------------------------------------------------------------------
+// Euclidean clustering: joins every pair of indexed points of `g` with d2 < r2 (strict) in a union-find over sorted
+// positions (`parent`, g.n ints) and writes root_of[original index] = original index of the set's root point
+// (entries of non-indexed points are left untouched: pre-set them to -1).
+void launch_cluster_unions(const GridView& g, float r2, int* parent, int* root_of, const FarWork& fw, cudaStream_t stream);
+
+// pcl::VoxelGrid::applyFilter on strided points (xyz first; rgba word at byte 16 when stride >= 20).  Writes one
+// centroid point per occupied voxel to d_out (ascending voxel index, same stride) and returns their number.
+// *overflow: the voxel indices would not fit 32 bits ("leaf size too small"): nothing is written, n is returned.
+class VoxelGrid {
+ public:
+  int64_t run(const unsigned char* d_in, int64_t n, int64_t stride, float leaf, unsigned char* d_out, cudaStream_t stream,
+              bool* overflow);
+
+ private:
+  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, hist_, scan_tmp_, starts_;
+  DevBuf<unsigned> scratch_;
+};
+
 // second-order moments of the objective around T0 (cost.cu): 74 sums from which every later f / df evaluation of the
 // outer iteration is host arithmetic.  `partials` holds moments_grid_blocks * 80 doubles, `ticket` one zeroed uint.
 constexpr int kMomentSums = 74;

@@ -27,11 +27,16 @@
 //   * getPointCloudDifference .......... PCL segmentation/impl/segment_differences.hpp, reference
 //                                        src/Filter.cpp:176-189
 //   * computeCloudResolution ........... reference src/Utils.cpp:145-174
+//   * extractEuclideanClusters ......... PCL segmentation/impl/extract_clusters.hpp, reference
+//                                        src/FODDetector.cpp:45-58
+//   * VoxelGrid::applyFilter ........... PCL filters/impl/voxel_grid.hpp + common/impl/accumulators.hpp, reference
+//                                        src/Filter.cpp:91-105
 //
 // Build (parity):  g++ -O2 -ffp-contract=off -fPIC -shared  (single thread, no FMA contraction)
 // Build (timing):  g++ -O3 -march=native -fopenmp -fPIC -shared  (all host cores over points)
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -246,6 +251,10 @@ class KdTree {
     if (!nodes_.empty()) count(0, q, r2, cap, found);
     return found;
   }
+  // all indexed points with d2 < r2 (strict, as FLANN's RadiusResultSet), appended to `out` in no particular order
+  void radius(const float* q, float r2, std::vector<int>& out) const {
+    if (!nodes_.empty()) collect(0, q, r2, out);
+  }
   // k nearest, sorted ascending by (d2, index); returns number found
   int knn(const float* q, int k, int* out_i, float* out_d) const {
     int found = 0;
@@ -301,6 +310,19 @@ class KdTree {
     const int near = diff < 0.f ? nd.left : nd.right, far = diff < 0.f ? nd.right : nd.left;
     count(near, q, r2, cap, found);
     if (found < cap && !(diff * diff >= r2)) count(far, q, r2, cap, found);
+  }
+
+  void collect(int id, const float* q, float r2, std::vector<int>& out) const {
+    const Node& nd = nodes_[id];
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi; ++i)
+        if (sqdist(q, pts_ + 3 * idx_[i]) < r2) out.push_back(idx_[i]);
+      return;
+    }
+    const float diff = q[nd.axis] - nd.split;
+    const int near = diff < 0.f ? nd.left : nd.right, far = diff < 0.f ? nd.right : nd.left;
+    collect(near, q, r2, out);
+    if (!(diff * diff >= r2)) collect(far, q, r2, out);
   }
 
   void search1(int id, const float* q, int& bi, float& bd) const {
@@ -1377,6 +1399,142 @@ int orc_normal_validity(const float* xyz, int n, double radius, unsigned char* m
     kept += ok ? 1 : 0;
   }
   return kept;
+}
+
+// ---- pcl::EuclideanClusterExtraction::extract (reference src/FODDetector.cpp:45-58): extractEuclideanClusters
+//      restated literally - for every unprocessed point a seed queue is grown with the radius neighbours
+//      (d2 < float(tolerance^2), the query itself comes first in the sorted result and is skipped) of each queued
+//      point; a queue of min_size..max_size points becomes a cluster (indices sorted); extract() then sorts the
+//      clusters by size, largest first.  std::sort leaves the order of equal-sized clusters unspecified: here they keep
+//      their discovery order (lowest seed index first).  labels[i] = rank of the cluster of point i, -1 = none.
+//      Non-finite points are not in the tree and never seeded (the reference's difference cloud is dense).
+int orc_euclidean_clusters(const float* xyz, int n, double tolerance, int min_size, int max_size, int* labels) {
+  for (int i = 0; i < n; ++i) labels[i] = -1;
+  if (n <= 0) return 0;
+  if (max_size <= 0) max_size = std::numeric_limits<int>::max();
+  KdTree tree(xyz, n);
+  const float r2 = (float)(tolerance * tolerance);
+  std::vector<char> processed((size_t)n, 0);
+  std::vector<std::vector<int>> clusters;
+  std::vector<int> nn;
+  for (int i = 0; i < n; ++i) {
+    if (processed[i]) continue;
+    const float* p = xyz + 3 * i;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    std::vector<int> seed_queue;
+    size_t sq_idx = 0;
+    seed_queue.push_back(i);
+    processed[i] = 1;
+    while (sq_idx < seed_queue.size()) {
+      nn.clear();
+      tree.radius(xyz + 3 * seed_queue[sq_idx], r2, nn);
+      for (size_t j = 0; j < nn.size(); ++j) {
+        if (processed[nn[j]]) continue;  // includes the query itself (nn_start_idx = 1 in PCL)
+        seed_queue.push_back(nn[j]);
+        processed[nn[j]] = 1;
+      }
+      ++sq_idx;
+    }
+    if ((int64_t)seed_queue.size() >= min_size && (int64_t)seed_queue.size() <= max_size) {
+      std::sort(seed_queue.begin(), seed_queue.end());
+      clusters.push_back(std::move(seed_queue));
+    }
+  }
+  std::stable_sort(clusters.begin(), clusters.end(),
+                   [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+  for (size_t k = 0; k < clusters.size(); ++k)
+    for (int idx : clusters[k]) labels[idx] = (int)k;
+  return (int)clusters.size();
+}
+
+// ---- pcl::VoxelGrid<PointXYZRGB>::applyFilter with leaf (l, l, l), downsample_all_data_ = true,
+//      min_points_per_voxel_ = 0 (reference src/Filter.cpp:91-105).  `pts` holds n points of `stride` bytes (xyz
+//      floats first; when stride >= 20 the packed rgba word sits at byte 16 as in PointXYZRGB).  One output point per
+//      occupied voxel in ascending voxel index: xyz = float sum / count (AccumulatorXYZ), rgba channels =
+//      uint32(float sum / count) (AccumulatorRGBA), data[3] = 1, remaining bytes 0.  PCL sorts the (voxel, point)
+//      pairs with std::sort on the voxel index alone, which leaves the order inside a voxel unspecified; here it is
+//      the original point order (a stable sort), which fixes the float summation order.
+//      Returns the number of output points, or -1 when PCL would refuse the leaf size (index overflow) and copy
+//      the input through.
+int64_t orc_voxel_grid(const unsigned char* pts, int64_t n, int64_t stride, double leaf_size, unsigned char* out) {
+  const float leaf = (float)leaf_size;
+  const float inv = 1.0f / leaf;
+  float min_p[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, max_p[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int64_t n_valid = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = reinterpret_cast<const float*>(pts + i * stride);
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    ++n_valid;
+    for (int a = 0; a < 3; ++a) {
+      min_p[a] = std::min(min_p[a], p[a]);
+      max_p[a] = std::max(max_p[a], p[a]);
+    }
+  }
+  if (n_valid == 0) return 0;
+  const int64_t dx = (int64_t)((max_p[0] - min_p[0]) * inv) + 1;
+  const int64_t dy = (int64_t)((max_p[1] - min_p[1]) * inv) + 1;
+  const int64_t dz = (int64_t)((max_p[2] - min_p[2]) * inv) + 1;
+  // PCL tests dx*dy*dz (int64) against INT32_MAX; the running product is checked here so that it cannot wrap
+  const int64_t lim = (int64_t)std::numeric_limits<int32_t>::max();
+  if (dx > lim || dx * dy > lim || dx * dy * dz > lim) return -1;
+  int min_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a) {
+    min_b[a] = (int)std::floor(min_p[a] * inv);
+    const int max_b = (int)std::floor(max_p[a] * inv);
+    div_b[a] = max_b - min_b[a] + 1;
+  }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<unsigned, int64_t>> index_vector;
+  index_vector.reserve((size_t)n_valid);
+  for (int64_t i = 0; i < n; ++i) {
+    const float* p = reinterpret_cast<const float*>(pts + i * stride);
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    const int ijk0 = (int)(std::floor(p[0] * inv) - (float)min_b[0]);
+    const int ijk1 = (int)(std::floor(p[1] * inv) - (float)min_b[1]);
+    const int ijk2 = (int)(std::floor(p[2] * inv) - (float)min_b[2]);
+    index_vector.emplace_back((unsigned)(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]), i);
+  }
+  std::stable_sort(index_vector.begin(), index_vector.end(),
+                   [](const std::pair<unsigned, int64_t>& a, const std::pair<unsigned, int64_t>& b) { return a.first < b.first; });
+  int64_t n_out = 0;
+  size_t first = 0;
+  while (first < index_vector.size()) {
+    size_t last = first + 1;
+    while (last < index_vector.size() && index_vector[last].first == index_vector[first].first) ++last;
+    float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f, sa = 0.f;
+    for (size_t k = first; k < last; ++k) {
+      const unsigned char* pt = pts + index_vector[k].second * stride;
+      const float* p = reinterpret_cast<const float*>(pt);
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+      if (stride >= 20) {
+        uint32_t c;
+        std::memcpy(&c, pt + 16, 4);
+        sb += (float)(c & 255u);
+        sg += (float)((c >> 8) & 255u);
+        sr += (float)((c >> 16) & 255u);
+        sa += (float)(c >> 24);
+      }
+    }
+    const float cnt = (float)(last - first);
+    unsigned char* o = out + n_out * stride;
+    std::memset(o, 0, (size_t)stride);
+    const float c3[3] = {sx / cnt, sy / cnt, sz / cnt};
+    std::memcpy(o, c3, 12);
+    if (stride >= 16) {
+      const float one = 1.0f;
+      std::memcpy(o + 12, &one, 4);
+    }
+    if (stride >= 20) {
+      const uint32_t c = ((uint32_t)(sa / cnt) << 24) | ((uint32_t)(sr / cnt) << 16) | ((uint32_t)(sg / cnt) << 8) |
+                         (uint32_t)(sb / cnt);
+      std::memcpy(o + 16, &c, 4);
+    }
+    ++n_out;
+    first = last;
+  }
+  return n_out;
 }
 
 }  // extern "C"

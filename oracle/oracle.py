@@ -221,6 +221,25 @@ class Oracle:
                                          _p(mask, c_ubyte_p))
         return mask, int(n)
 
+    def euclidean_clusters(self, xyz, tolerance, min_size=1, max_size=0):
+        """pcl::EuclideanClusterExtraction::extract: (labels in PCL's cluster order, -1 = none; n_clusters)"""
+        a = _xyz(xyz) if len(xyz) else np.zeros((0, 3), np.float32)
+        labels = np.full(len(a), -1, np.int32)
+        self.lib.orc_euclidean_clusters.restype = ctypes.c_int
+        nc = self.lib.orc_euclidean_clusters(_p(a, c_float_p), ctypes.c_int(len(a)), ctypes.c_double(tolerance),
+                                             ctypes.c_int(int(min_size)), ctypes.c_int(int(max_size)), _p(labels, c_int_p))
+        return labels, int(nc)
+
+    def voxel_grid(self, cloud, leaf_size):
+        """pcl::VoxelGrid on a float32 [n, 3|4|8] array (8 = PointXYZRGB layout); None when PCL would refuse the leaf"""
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        stride = a.shape[1] * 4
+        out = np.zeros_like(a)
+        self.lib.orc_voxel_grid.restype = ctypes.c_int64
+        m = self.lib.orc_voxel_grid(ctypes.c_void_p(a.ctypes.data), ctypes.c_int64(len(a)), ctypes.c_int64(stride),
+                                    ctypes.c_double(leaf_size), ctypes.c_void_p(out.ctypes.data))
+        return None if m < 0 else out[: int(m)]
+
     def resolution(self, xyz):
         xyz = _xyz(xyz)
         return float(self.lib.orc_resolution(_p(xyz, c_float_p), len(xyz)))

@@ -7,12 +7,15 @@
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <type_traits>
 
+#include "FODDetector_b200.hpp"
 #include "GICPAlignment_b200.hpp"
 
 typedef GICPAlignment::PointCloudRGB PointCloudRGB;
 typedef GICPAlignment::CloudPtr CloudPtr;
 typedef GICPAlignment::Matrix4f Matrix4f;
+typedef std::remove_reference<decltype(PointCloudRGB().points[0])>::type PointT;
 
 static int g_failed = 0;
 #define EXPECT_TRUE(cond)                                              \
@@ -161,6 +164,53 @@ int main(int argc, char** argv) {
     EXPECT_TRUE(same->points.empty());
     gicpb_shim::removeFromCloud(moved, sourceRGB, 0.0344, moved);  // output aliases the input
     EXPECT_TRUE(moved->points.size() == out->points.size());
+  }
+  {  // test/test_fod_detector.cpp:32-72 testFODClustering and :75-90 testEmptyCloud
+    auto cubes = [](CloudPtr cloud, float pos, float dim, float step) {
+      PointT p_rgb;
+      for (float i = pos; i < pos + dim; i += step)
+        for (float j = pos; j < pos + dim; j += step)
+          for (float k = pos; k < pos + dim; k += step) {
+            p_rgb.x = i; p_rgb.y = j; p_rgb.z = k;
+            p_rgb.r = 255; p_rgb.g = 255; p_rgb.b = 255;
+            cloud->points.push_back(p_rgb);
+          }
+      cloud->width = (uint32_t)cloud->points.size();
+    };
+    CloudPtr cloudRGB(new PointCloudRGB);
+    cubes(cloudRGB, 0, 3, 0.1f);
+    cubes(cloudRGB, 10, 3, 0.1f);
+    cubes(cloudRGB, 20, 3, 0.1f);
+    int min_fod_points = 3;
+    double voxelize_factor = 3;
+    double th = 4e-3 * voxelize_factor;
+    FODDetector fod_detector(cloudRGB, th * 10, min_fod_points);
+    fod_detector.clusterPossibleFODs();
+    std::vector<CloudPtr> fods_cloud_array;
+    int num_of_fods = fod_detector.fodIndicesToPointCloud(fods_cloud_array);
+    EXPECT_TRUE(num_of_fods == 3);
+    EXPECT_TRUE(fods_cloud_array.size() == 3);
+    std::vector<FODDetector::PointIndices> idx;
+    fod_detector.getFODIndices(idx);
+    size_t total = 0;
+    for (size_t k = 0; k < idx.size(); ++k) {
+      total += idx[k].indices.size();
+      EXPECT_TRUE(k == 0 || idx[k].indices.size() <= idx[k - 1].indices.size());  // largest cluster first
+      EXPECT_TRUE(fods_cloud_array[k]->points.size() == idx[k].indices.size() && fods_cloud_array[k]->is_dense);
+    }
+    std::printf("RESULT fod_clusters %d points %zu of %zu\n", num_of_fods, total, cloudRGB->points.size());
+    EXPECT_TRUE(total == cloudRGB->points.size());
+    CloudPtr empty_cloud(new PointCloudRGB);
+    FODDetector fod_empty(empty_cloud, th * 10, min_fod_points);
+    fod_empty.clusterPossibleFODs();
+    std::vector<CloudPtr> none;
+    EXPECT_TRUE(fod_empty.fodIndicesToPointCloud(none) == 0 && none.empty());
+    // Filter::downsampleCloud, test/test_filter.cpp:68-83: fewer points, spread further apart
+    CloudPtr down(new PointCloudRGB);
+    gicpb_shim::downsampleCloud(cloudRGB, down, 0.25);
+    std::printf("RESULT downsample %zu -> %zu\n", cloudRGB->points.size(), down->points.size());
+    EXPECT_TRUE(!down->points.empty() && down->points.size() < cloudRGB->points.size());
+    EXPECT_TRUE(down->points[0].r == 255 && down->points[0].a == 255 && down->points[0].w == 1.f && down->is_dense);
   }
   std::printf("RESULT failed %d\n", g_failed);
   return g_failed ? 1 : 0;

@@ -24,7 +24,7 @@ def test_shim_compiles_and_links(tmp_path):
     exe = build(tmp_path)
     out = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
     for sym in ("gicpb_create", "gicpb_align", "gicpb_set_source", "gicpb_set_target", "gicpb_fitness",
-                "gicpb_transform_cloud", "gicpb_cloud_difference"):
+                "gicpb_transform_cloud", "gicpb_cloud_difference", "gicpb_euclidean_clusters", "gicpb_voxel_grid"):
         assert sym in out
     # the reference's public surface is all there (include/GICPAlignment.h:47-145)
     hdr = open(os.path.join(ROOT, "include", "GICPAlignment_b200.hpp")).read()
@@ -54,6 +54,7 @@ def test_reference_gtests_through_the_cpp_shim(tmp_path, cube_pair, oracle):
             parts = line.split()
             res[parts[1]] = parts[2:]
     assert res["failed"] == ["0"]
+    assert res["fod_clusters"][0] == "3"      # test/test_fod_detector.cpp:70 ASSERT_EQ(num_of_fods, 3)
     # testRun parameters (gate 5, tf_eps 5e-4): same transform as the oracle, inside the north_star tolerances
     T_gpu = np.array([float(v) for v in res["run_transform"]]).reshape(4, 4)
     ref = oracle.align(src, tgt, default_params(max_corr_distance=5.0, transformation_epsilon=5e-4))
