@@ -93,6 +93,15 @@ int gicpb_get_params(const gicpb_ctx* ctx, gicpb_params* p);
 int gicpb_nccl_unique_id(const char* libnccl_path, unsigned char id_out[128]);
 int gicpb_comm_init(gicpb_ctx* ctx, const char* libnccl_path, int rank, int world, const unsigned char id[128]);
 int gicpb_comm_rank(const gicpb_ctx* ctx, int* rank, int* world);
+/* Optional, after gicpb_comm_init on every rank: fuse the cross-GPU sum of the 14 cost sums INTO the cost kernel over
+ * NVLink peer memory (the kernel's last block stores its sums into every rank's slot block, raises a flag, waits for
+ * the other ranks' flags and adds the slots in rank order), replacing the ncclAllReduce + copy per evaluation.
+ * gicpb_peer_export returns this rank's cudaIpcMemHandle_t (64 bytes); the caller gathers the handles of all ranks
+ * (rank order, 64 bytes each) and passes them to gicpb_peer_import.  All ranks must be processes on one node with
+ * peer access between their GPUs; on failure the context keeps using NCCL. */
+int gicpb_peer_export(gicpb_ctx* ctx, unsigned char handle_out[64]);
+int gicpb_peer_import(gicpb_ctx* ctx, const unsigned char* handles, int world);
+int gicpb_peer_disable(gicpb_ctx* ctx); /* back to ncclAllReduce (call on every rank) */
 
 /* ---- clouds: upload once, index on the GPU (replaces setInputTarget / setInputSource and the two FLANN
  *      kd-tree builds, src/GICPAlignment.cpp:89-90; PCL Registration::initCompute[Reciprocal]) ------- */

@@ -81,6 +81,9 @@ _SIGNATURES = [
     ("gicpb_nccl_unique_id", ctypes.c_int, [ctypes.c_char_p, c_uint8_p]),
     ("gicpb_comm_init", ctypes.c_int, [_VOID_P, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, c_uint8_p]),
     ("gicpb_comm_rank", ctypes.c_int, [_VOID_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    ("gicpb_peer_export", ctypes.c_int, [_VOID_P, c_uint8_p]),
+    ("gicpb_peer_import", ctypes.c_int, [_VOID_P, c_uint8_p, ctypes.c_int]),
+    ("gicpb_peer_disable", ctypes.c_int, [_VOID_P]),
     ("gicpb_set_target", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     ("gicpb_set_source", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     ("gicpb_compute_covariances", ctypes.c_int, [_VOID_P]),
@@ -228,6 +231,20 @@ class Engine:
         if rc != GICPB_OK:
             raise GicpError(rc, "gicpb_nccl_unique_id failed")
         return bytes(buf)
+
+    def peer_export(self):
+        buf = (ctypes.c_uint8 * 64)()
+        self._check(self.lib.gicpb_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_import(self, handles):
+        """handles: list of the 64-byte handles of all ranks, in rank order"""
+        blob = b"".join(handles)
+        buf = (ctypes.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._check(self.lib.gicpb_peer_import(self.h, buf, len(handles)))
+
+    def peer_disable(self):
+        self._check(self.lib.gicpb_peer_disable(self.h))
 
     def comm_init(self, rank, world, unique_id, libnccl=None):
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)

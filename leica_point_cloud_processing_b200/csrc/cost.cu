@@ -64,12 +64,12 @@ __device__ __forceinline__ void add_pair(const PairData<MT>& d, const Rigid& T, 
   acc[13] += 1.0;
 }
 
-template <typename MT>
+template <typename MT, bool kPeer>
 __global__ void __launch_bounds__(kCostThreads, 2) cost_kernel(const float4* __restrict__ src, int lo, int n,
                                                                 const float4* __restrict__ pair_tgt,
                                                                 const MT* __restrict__ maha, Rigid T,
                                                                 double* __restrict__ partials, unsigned* __restrict__ ticket,
-                                                                double* __restrict__ out) {
+                                                                double* __restrict__ out, PeerReduce pr) {
   double acc[kCostSums];
 #pragma unroll
   for (int c = 0; c < kCostSums; ++c) acc[c] = 0.0;
@@ -121,13 +121,52 @@ __global__ void __launch_bounds__(kCostThreads, 2) cost_kernel(const float4* __r
     for (int b = grp; b < (int)gridDim.x; b += kCostThreads / 16) v += __ldcg(&partials[(size_t)b * 16 + c]);
   red[grp][c] = v;
   __syncthreads();
+  double s = 0.0;
   if (threadIdx.x < kCostSums) {
-    double s = 0.0;
 #pragma unroll
     for (int gi = 0; gi < kCostThreads / 16; ++gi) s += red[gi][threadIdx.x];
-    out[threadIdx.x] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
+  if (!kPeer) {
+    if (threadIdx.x < kCostSums) out[threadIdx.x] = s;
+    return;
+  }
+  // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
+  const int set = (int)(pr.seq & 1u);
+  if (threadIdx.x < kCostSums)
+    for (int p = 0; p < pr.world; ++p) {
+      volatile double* dst = &pr.peers[p]->vals[set][pr.rank][threadIdx.x];
+      *dst = s;
+    }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pr.world) {
+    volatile unsigned* f = &pr.peers[threadIdx.x]->flag[set][pr.rank];
+    *f = pr.seq;  // thread p tells rank p that this rank's sums of evaluation `seq` are in place
+  }
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < pr.world) {
+    volatile unsigned* f = &pr.peers[pr.rank]->flag[set][threadIdx.x];
+    const long long t0 = clock64();
+    while (*f != pr.seq) {
+      if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer never launched this evaluation
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x < kCostSums) {
+    double t = 0.0;
+    for (int r = 0; r < pr.world; ++r) {
+      volatile double* v = &pr.peers[pr.rank]->vals[set][r][threadIdx.x];
+      t += *v;
+    }
+    out[threadIdx.x] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
+  }
 }
 
 
@@ -244,13 +283,25 @@ int cost_grid_blocks(int n, int num_sms) {
 }
 
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
-                 const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream) {
-  if (maha_fp32)
-    cost_kernel<float><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const float*)maha, T, partials,
-                                                            ticket, out14);
-  else
-    cost_kernel<double><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const double*)maha, T, partials,
-                                                             ticket, out14);
+                 const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream,
+                 const PeerReduce* peer) {
+  PeerReduce pr{};
+  if (peer) pr = *peer;
+  if (maha_fp32) {
+    if (peer)
+      cost_kernel<float, true><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const float*)maha, T, partials,
+                                                                    ticket, out14, pr);
+    else
+      cost_kernel<float, false><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const float*)maha, T, partials,
+                                                                     ticket, out14, pr);
+  } else {
+    if (peer)
+      cost_kernel<double, true><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const double*)maha, T, partials,
+                                                                     ticket, out14, pr);
+    else
+      cost_kernel<double, false><<<blocks, kCostThreads, 0, stream>>>(src, lo, n, pair_tgt, (const double*)maha, T, partials,
+                                                                      ticket, out14, pr);
+  }
   GICPB_LAUNCHED();
 }
 

@@ -201,6 +201,10 @@ struct gicpb_ctx {
   NcclApi* nccl = nullptr;
   NcclApi::comm_t comm = nullptr;
   int rank = 0, world = 1;
+  // fused cost + cross-GPU sum over peer memory (kernels.hpp PeerReduce); falls back to ncclAllReduce when not set up
+  PeerSlots* peer_own = nullptr;
+  PeerReduce peer{};
+  bool peer_ready = false;
 
   // accounting
   double ms_corr = 0, ms_cost = 0;
@@ -399,16 +403,21 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
   const Rigid T = rigid_from_rowmajor(T16);
   const int n = c->shard_hi - c->shard_lo;
   const int blocks = cost_grid_blocks(n, c->num_sms);
-  double* out = (c->world > 1) ? c->d_sums.get() : c->h_sums_dev;
+  const bool fused = c->world > 1 && c->peer_ready;
+  double* out = (c->world > 1 && !fused) ? c->d_sums.get() : c->h_sums_dev;
+  if (fused) {
+    if (++c->peer.seq == 0u) c->peer.seq = 1u;
+  }
   launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32, T,
-              c->partials.get(), c->ticket.get(), out, blocks, c->stream);
-  if (c->world > 1) {
+              c->partials.get(), c->ticket.get(), out, blocks, c->stream, fused ? &c->peer : nullptr);
+  if (c->world > 1 && !fused) {
     all_reduce_sum(c, c->d_sums.get(), kCostSums);
     GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), kCostSums * sizeof(double), cudaMemcpyDeviceToHost,
                                c->stream));
   }
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < kCostSums; ++i) sums[i] = c->h_sums[i];
+  if (fused && std::isnan(sums[13])) throw NcclError("peer-memory reduction timed out: a rank did not launch this evaluation");
   ++c->cost_evals;
 }
 
@@ -612,6 +621,10 @@ void gicpb_destroy(gicpb_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->h_mom) cudaFreeHost(c->h_mom);
+  if (c->peer.world > 1)
+    for (int r = 0; r < c->peer.world; ++r)
+      if (r != c->rank && c->peer.peers[r]) cudaIpcCloseMemHandle(c->peer.peers[r]);
+  if (c->peer_own) cudaFree(c->peer_own);
   if (c->h_far) cudaFreeHost(c->h_far);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -670,6 +683,50 @@ int gicpb_comm_init(gicpb_ctx* c, const char* libnccl_path, int rank, int world,
     c->pairs_valid = false;
     update_shard(c);
   });
+}
+
+int gicpb_peer_export(gicpb_ctx* c, unsigned char handle_out[64]) {
+  return guarded(c, [&] {
+    if (!handle_out) throw ArgError("null handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!c->peer_own) {
+      GICPB_CUDA(cudaMalloc(&c->peer_own, sizeof(PeerSlots)));
+      GICPB_CUDA(cudaMemset(c->peer_own, 0, sizeof(PeerSlots)));
+    }
+    cudaIpcMemHandle_t h;
+    GICPB_CUDA(cudaIpcGetMemHandle(&h, c->peer_own));
+    std::memcpy(handle_out, &h, 64);
+  });
+}
+
+int gicpb_peer_import(gicpb_ctx* c, const unsigned char* handles, int world) {
+  return guarded(c, [&] {
+    if (!handles) throw ArgError("null handles");
+    if (world != c->world || world < 2 || world > kMaxPeers) throw ArgError("world must match gicpb_comm_init (2..16)");
+    if (!c->peer_own) throw StateError("gicpb_peer_export must be called first");
+    c->peer_ready = false;
+    for (int r = 0; r < world; ++r) {
+      if (r == c->rank) {
+        c->peer.peers[r] = c->peer_own;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + 64 * (size_t)r, 64);
+      void* p = nullptr;
+      GICPB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      c->peer.peers[r] = static_cast<PeerSlots*>(p);
+    }
+    c->peer.rank = c->rank;
+    c->peer.world = world;
+    c->peer.seq = 0u;
+    c->peer_ready = true;
+  });
+}
+
+int gicpb_peer_disable(gicpb_ctx* c) {
+  if (!c) return GICPB_E_BADARG;
+  c->peer_ready = false;  // back to ncclAllReduce; mapped handles stay open until gicpb_destroy
+  return GICPB_OK;
 }
 
 int gicpb_comm_rank(const gicpb_ctx* c, int* rank, int* world) {

@@ -105,10 +105,30 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
 // ---- cost.cu ------------------------------------------------------------------------------------------
 constexpr int kCostSums = 14;  // f, g_t[3], Rsum[9], pair count
 int cost_grid_blocks(int n, int num_sms);
+
+// Cross-GPU sum of the 14 cost sums INSIDE the cost kernel, over NVLink peer memory (no collective call, no extra
+// launch): every rank owns one PeerSlots block in device memory that all ranks have mapped (cudaIpc).  The last block
+// of a rank's cost kernel stores its 14 sums into slot [seq & 1][rank] of EVERY rank's block (peer stores), fences,
+// raises the slot's flag to `seq`, waits until all `world` flags of its OWN block show `seq`, and adds the slots in
+// rank order - the same order on every rank, so all ranks hold bit-identical sums and the host optimisers stay in
+// lock step.  Two slot sets alternate: a rank can run at most one evaluation ahead of the slowest.
+constexpr int kMaxPeers = 16;
+struct PeerSlots {
+  double vals[2][kMaxPeers][16];
+  unsigned flag[2][kMaxPeers];
+};
+struct PeerReduce {
+  PeerSlots* peers[kMaxPeers];  // peers[r] = rank r's block as mapped in this process (peers[rank] = own)
+  int rank, world;
+  unsigned seq;                 // evaluation counter, identical on all ranks, never 0
+};
 // sums over this rank's pairs; `partials` holds cost_grid_blocks * kCostSums doubles, `ticket` one zeroed uint.
 // out14 may be device memory or mapped pinned host memory.
+// peer != nullptr: out14 receives the sum over all ranks (see PeerReduce); a peer that does not show up within ~2 s
+// makes every entry NaN.
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
-                 const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream);
+                 const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream,
+                 const PeerReduce* peer = nullptr);
 
 // ---- segment.cu -----------------------------------------------------------------------------------------
 // Euclidean clustering: joins every pair of indexed points of `g` with d2 < r2 (strict) in a union-find over sorted

@@ -1,8 +1,9 @@
 """Multi-GPU plumbing: one process per GPU (torchrun), source points sharded by rank, target replicated.
 
 torch.distributed is used only to agree on the NCCL unique id (works over any backend, e.g. gloo on CPU); the
-per-evaluation all-reduce of the 14 partial sums is issued by the engine itself on its own NCCL communicator
-(csrc/engine.cu run_cost), so no Python sits on the evaluation path.
+per-evaluation sum of the 14 partial sums over the ranks happens inside the engine (csrc/engine.cu run_cost): fused
+into the cost kernel over NVLink peer memory when the ranks could map each other's slot blocks, else one
+ncclAllReduce on the engine's own communicator.  No Python sits on the evaluation path.
 """
 import os
 
@@ -33,9 +34,40 @@ def exchange_unique_id(make_id, rank, group=None):
     return bytes(buf.cpu().tolist())
 
 
-def init_engine_comm(engine, rank, world, group=None):
-    """Create the engine's NCCL communicator across the ranks of an initialised torch.distributed job."""
+def init_engine_comm(engine, rank, world, group=None, peer_memory=True):
+    """Create the engine's NCCL communicator across the ranks of an initialised torch.distributed job and, when the
+    GPUs can map each other's memory, switch the per-evaluation sum to the fused peer-memory path.  Returns True
+    when the fused path is on."""
     if world <= 1:
-        return
+        return False
     uid = exchange_unique_id(engine.nccl_unique_id, rank, group)
     engine.comm_init(rank, world, uid)
+    if peer_memory and os.environ.get("GICPB_NO_PEER", "0") != "1":
+        return enable_peer_reduction(engine, rank, world, group)
+    return False
+
+
+def enable_peer_reduction(engine, rank, world, group=None):
+    """Fuse the per-evaluation cross-GPU sum into the cost kernel over NVLink peer memory (include/gicp_b200.h
+    gicpb_peer_export / gicpb_peer_import).  Every rank either enables it or none does (an all-gathered vote), so a
+    node without peer access simply stays on ncclAllReduce.  Returns True when enabled."""
+    import torch.distributed as dist
+
+    try:
+        mine = engine.peer_export()
+    except Exception:
+        mine = None
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    ok = all(h is not None for h in handles)
+    if ok:
+        try:
+            engine.peer_import(handles)
+        except Exception:
+            ok = False
+    votes = [None] * world
+    dist.all_gather_object(votes, ok, group=group)
+    if not all(votes):
+        engine.peer_disable()
+        return False
+    return True
