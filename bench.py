@@ -180,8 +180,8 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     eng = Engine(local_rank)
-    init_engine_comm(eng, rank, world)
-    eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32)
+    fused_peer = init_engine_comm(eng, rank, world)
+    eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32, cost_moments=args.cost_moments)
 
     def step(tgt_buf, src_buf):
         eng.set_target(tgt_buf)
@@ -289,6 +289,60 @@ def run_ours(args):
                  "points_per_cell": ginfo["n_indexed"] / max(ginfo["n_cells_occupied"], 1)},
     }
 
+    # ---- secondary measurements (not part of the timed steps above) ----------------------------------------------
+    def dev_ms(fn, iters=3):
+        best = None
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(estream)
+            out = fn()
+            e1.record(estream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best, out
+
+    if world == 1:
+        from leica_point_cloud_processing_b200 import synth as _synth
+        # the opt-in moments mode: same objective from 74 moments per outer iteration (include/gicp_b200.h cost_moments)
+        if not args.cost_moments:
+            eng.set_params(cost_moments=1)
+            m_times, (m_res, m_fit), m_queries, _, _ = timed(d_tgt, d_src, max(2, args.steps // 2), 1)
+            eng.set_params(cost_moments=0)
+            extra["cost_moments_mode"] = {
+                "ms_per_step": 1e3 * sum(m_times) / len(m_times), "value": m_queries / sum(m_times),
+                "outer_iterations": m_res["outer_iterations"], "cost_evaluations_on_host": m_res["cost_evaluations"],
+                "vs_default_rot_rad": _synth.rotation_error_rad(m_res["transform"], res["transform"]),
+                "vs_default_trans_m": _synth.translation_error(m_res["transform"], res["transform"]),
+                "note": "opt-in: exact instead of float-rounded T*p; PCL's line search amplifies the 1e-8 relative "
+                        "difference, so the result agrees with the default to the stopping slack, not to the parity bar"}
+        # SURVEY 8a row a13 and 8f rows 1, 3 on the same data: difference of the aligned scan (+ 20 FOD blobs) against
+        # the CAD cloud, clusters of the difference cloud, voxel-grid downsample of the scan as PointXYZRGB rows
+        aligned = _synth.apply_rigid(T_star, src)
+        with_fod, _ = _synth.add_fod_blobs(aligned.astype(np.float32), n_blobs=20, seed=999, length=dims[0], width=dims[1])
+        d_fod = torch.from_numpy(np.ascontiguousarray(with_fod, dtype=np.float32)).cuda()
+        thr = 4e-3 * 0.1
+        ms_diff, (mask, kept) = dev_ms(lambda: eng.cloud_difference(d_fod, d_tgt, thr))
+        diff_cloud = d_fod[mask.bool()].contiguous()
+        ms_clu, (labels, n_clu) = dev_ms(lambda: eng.euclidean_clusters(diff_cloud, thr * 100, 3, 0))
+        rgb = torch.zeros((n, 8), dtype=torch.float32, device="cuda")
+        rgb[:, :3] = d_src
+        rgb[:, 3] = 1.0
+        eng.set_target(d_src)
+        leaf = 10.0 * eng.cloud_resolution(0)          # src/LeicaStateMachine.cpp:61-65: leaf_size_factor 10
+        eng.set_target(d_tgt)
+        ms_vox, vox = dev_ms(lambda: eng.voxel_grid(rgb, leaf))
+        n_fod = int(d_fod.shape[0])
+        extra["fod_pipeline"] = {
+            "cloud_difference": dict(kern(ms_diff, 16.0 * n_fod + 16.0 * n + n_fod), points_in=n_fod, kept=int(kept),
+                                     includes="index build of the subtract cloud + difference kernels"),
+            "euclidean_clusters": {"ms": ms_clu, "points": int(diff_cloud.shape[0]), "clusters": int(n_clu),
+                                   "includes": "index build, union-find kernels, labels to the host, host grouping"},
+            "voxel_grid": dict(kern(ms_vox, 32.0 * n + 32.0 * int(vox.shape[0])), points_in=n, points_out=int(vox.shape[0]),
+                               leaf_m=float(leaf), includes="min/max, keys, radix sort, heads/scan, centroids"),
+        }
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from leica_point_cloud_processing_b200 import synth
@@ -324,6 +378,10 @@ def run_ours(args):
                        "l2": "256 MiB flush write between timed steps", "timing": "CUDA events on the engine's stream around "
                        "each step, barrier + synchronize on both sides, max over ranks; kernels by CUDA events on the same stream",
                        "mahalanobis": "fp32" if args.maha_fp32 else "fp64",
+                       "objective": "74 moments per outer iteration (cost_moments=1)" if args.cost_moments else
+                                    "one cost-kernel pass per evaluation (PCL's float T*p arithmetic)",
+                       "cross_gpu_sum": ("fused into the cost kernel over NVLink peer memory" if fused_peer else
+                                         "ncclAllReduce per evaluation") if world > 1 else "none (one GPU)",
                        "outer_iterations": res["outer_iterations"], "cost_evaluations": res["cost_evaluations"]},
             "align_ms": res["ms_total"], "fitness": fit,
             "e2e": {"value": e2e_value, "unit": "correspondences/s", "ms_per_step": 1e3 * e_total / len(e_times),
@@ -350,6 +408,7 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=1_000_000, help="cpu_baseline sample size")
     ap.add_argument("--ref-points", type=int, default=2_000_000, help="--impl reference sample cap")
     ap.add_argument("--maha-fp32", type=int, default=0)
+    ap.add_argument("--cost-moments", type=int, default=0, help="1: the opt-in moments objective (see gicp_b200.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
