@@ -20,6 +20,16 @@ for rep in range(2):
 ms_corr, _ = eng.bench_kernel(0, res["transform"], iters=3)
 ms_nn, _ = eng.bench_kernel(2, res["transform"], iters=3)
 ms_cost, _ = eng.bench_kernel(1, res["transform"], iters=3)
-mask, kept = eng.cloud_difference(synth.apply_rigid(T_star, src), tgt, 4e-4)
+with_fod, _ = synth.add_fod_blobs(synth.apply_rigid(T_star, src).astype(np.float32), n_blobs=20, seed=999)
+mask, kept = eng.cloud_difference(with_fod, tgt, 4e-4)
+labels, n_clusters = eng.euclidean_clusters(with_fod[mask.astype(bool)], 4e-2, 3, 0)
+rgb = np.zeros((n, 8), np.float32)
+rgb[:, :3] = src
+rgb[:, 3] = 1.0
+vox = eng.voxel_grid(rgb, 0.0185)
+eng.set_params(cost_moments=1)                                                          # the opt-in objective
+res_m = eng.align()
+eng.set_params(cost_moments=0)
 print("outer", res["outer_iterations"], "evals", res["cost_evaluations"], "ms", res["ms_total"], "far", res["corr_far_queries"], "fit", fit,
-      "corr_ms", ms_corr, "nn_ms", ms_nn, "cost_ms", ms_cost, "kept", kept, "launches", eng.launch_count())
+      "corr_ms", ms_corr, "nn_ms", ms_nn, "cost_ms", ms_cost, "kept", kept, "clusters", n_clusters, "voxels", len(vox),
+      "moments-mode ms", res_m["ms_total"], "launches", eng.launch_count())
