@@ -15,7 +15,9 @@ struct RotD {  // double 3x3, row-major: double(transformation_) top-left block 
 // neighbours (the queries are sorted by cell) and the warps of a block share cache lines.
 // flags must have room for the item count rounded up to kFarTile; tile_counter[0..1] (tile cursor, number of far
 // queries) are zeroed before each launch pair (reset_far).
-constexpr int kFarTile = 1024;  // 8 flags per thread of a 128-thread block
+constexpr int kFarTile = 256;   // 2 flags per thread of a 128-thread block: small tiles spread a clustered handful of
+                                // far queries (FOD blobs, a seam) over many blocks instead of serialising them in one
+constexpr int kFarFlagsPerThread = kFarTile / 128;
 struct FarWork {
   unsigned char* flags;
   unsigned* tile_counter;
@@ -37,10 +39,12 @@ __device__ __forceinline__ void far_for_each(const FarWork& fw, int n_items, F b
     __syncthreads();
     const int base = s_tile * kFarTile;
     if (base >= n_items) break;
-    // 8 consecutive flags per thread, in item order
-    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(fw.flags + base + threadIdx.x * 8) &
-                                 0x0101010101010101ull;
-    const int cnt = __popcll(w);
+    // kFarFlagsPerThread consecutive flags per thread, in item order
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < kFarFlagsPerThread; ++k)
+      w |= (unsigned)(fw.flags[base + threadIdx.x * kFarFlagsPerThread + k] & 1u) << k;
+    const int cnt = __popc(w);
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -55,8 +59,9 @@ __device__ __forceinline__ void far_for_each(const FarWork& fw, int n_items, F b
       s_n = off + cnt;
       s_next = 0;
     }
-    for (int k = 0; k < 8; ++k)
-      if ((w >> (8 * k)) & 1ull) s_items[off++] = base + threadIdx.x * 8 + k;
+#pragma unroll
+    for (int k = 0; k < kFarFlagsPerThread; ++k)
+      if ((w >> k) & 1u) s_items[off++] = base + threadIdx.x * kFarFlagsPerThread + k;
     __syncthreads();
     const int n = s_n;
     if (threadIdx.x == 0 && n) atomicAdd(fw.tile_counter + 1, (unsigned)n);  // statistics: queries answered here

@@ -52,9 +52,14 @@ struct UniteVisitor {
   float qx, qy, qz;
   float r2;
   unsigned self;  // sorted position of the query: every edge is handled once, from its larger end
+  int root;       // last known root of the query's set: a neighbour already hanging under it needs no union
   __device__ __forceinline__ float bound() const { return r2; }
   __device__ __forceinline__ void apply(unsigned i, const float4& p) {
-    if (i < self && dist2(qx, qy, qz, p) < r2) uf_unite(parent, (int)self, (int)i);
+    if (i < self && dist2(qx, qy, qz, p) < r2) {
+      if (*reinterpret_cast<volatile int*>(parent + i) == root) return;  // dense blobs: almost every pair ends here
+      uf_unite(parent, (int)self, (int)i);
+      root = uf_find(parent, (int)self);
+    }
   }
   __device__ __forceinline__ bool point(unsigned i) {
     apply(i, __ldg(&pts[i]));
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(kSegThreads, kFar ? 4 : 6) cluster_union_kerne
   auto body = [&](int i) {
     const float4 p = __ldg(&g.pts[i]);
     const Query q = make_query(g, p.x, p.y, p.z);
-    UniteVisitor v{g.pts, parent, p.x, p.y, p.z, r2, (unsigned)i};
+    UniteVisitor v{g.pts, parent, p.x, p.y, p.z, r2, (unsigned)i, i};
     if (kFar) {
       far_search(g, q, v);
       return;
