@@ -184,6 +184,10 @@ def run_ours(args):
     eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32, cost_moments=args.cost_moments)
 
     def step(tgt_buf, src_buf):
+        # host clouds: both uploads are queued on the copy stream, target first, so that the source uploads while the
+        # target is being indexed (no-op on device clouds)
+        eng.prefetch(0, tgt_buf)
+        eng.prefetch(1, src_buf)
         eng.set_target(tgt_buf)
         eng.set_source(src_buf)
         res = eng.align()

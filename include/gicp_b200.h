@@ -105,6 +105,11 @@ int gicpb_peer_disable(gicpb_ctx* ctx); /* back to ncclAllReduce (call on every 
 
 /* ---- clouds: upload once, index on the GPU (replaces setInputTarget / setInputSource and the two FLANN
  *      kd-tree builds, src/GICPAlignment.cpp:89-90; PCL Registration::initCompute[Reciprocal]) ------- */
+/* Optional hint for HOST clouds: start uploading cloud `which` (0 target, 1 source) on a copy stream now and return
+ * at once; a later gicpb_set_target / gicpb_set_source with the same (pointer, n, stride) uses that copy instead of
+ * uploading again, so the upload of one cloud overlaps the indexing of the other (pinned host memory overlaps; pageable
+ * memory is still correct).  The host buffer must stay valid and unchanged until that set call returns. */
+int gicpb_prefetch_cloud(gicpb_ctx* ctx, int which, const void* xyz, int64_t n, int64_t stride_bytes);
 int gicpb_set_target(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
 int gicpb_set_source(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
 /* kNN-k covariances of both clouds, regularised to (1, 1, gicp_epsilon) (PCL GICP::computeCovariances).

@@ -84,6 +84,7 @@ _SIGNATURES = [
     ("gicpb_peer_export", ctypes.c_int, [_VOID_P, c_uint8_p]),
     ("gicpb_peer_import", ctypes.c_int, [_VOID_P, c_uint8_p, ctypes.c_int]),
     ("gicpb_peer_disable", ctypes.c_int, [_VOID_P]),
+    ("gicpb_prefetch_cloud", ctypes.c_int, [_VOID_P, ctypes.c_int, _VOID_P, ctypes.c_int64, ctypes.c_int64]),
     ("gicpb_set_target", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     ("gicpb_set_source", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     ("gicpb_compute_covariances", ctypes.c_int, [_VOID_P]),
@@ -252,12 +253,29 @@ class Engine:
         self._check(self.lib.gicpb_comm_init(self.h, path, rank, world, buf))
 
     # ---- clouds ---------------------------------------------------------------------------------------
-    def set_target(self, cloud):
+    def prefetch(self, which, cloud):
+        """Start uploading a HOST cloud (0 target, 1 source) beside whatever runs next; the following set_target /
+        set_source of the same object uses that copy (gicpb_prefetch_cloud).  No-op for device clouds."""
         keep, ptr, n, stride, dev = _as_cloud(cloud)
+        if dev:
+            return
+        self._check(self.lib.gicpb_prefetch_cloud(self.h, int(which), ptr, n, stride))
+        if not hasattr(self, "_prefetched"):
+            self._prefetched = {}
+        self._prefetched[int(which)] = (cloud, keep, ptr, n, stride)  # same buffer (and pointer) for the set call
+
+    def _cloud_args(self, which, cloud):
+        pf = getattr(self, "_prefetched", {}).pop(which, None)
+        if pf is not None and pf[0] is cloud:
+            return pf[1], pf[2], pf[3], pf[4], 0
+        return _as_cloud(cloud)
+
+    def set_target(self, cloud):
+        keep, ptr, n, stride, dev = self._cloud_args(0, cloud)
         self._check(self.lib.gicpb_set_target(self.h, ptr, n, stride, dev))
 
     def set_source(self, cloud):
-        keep, ptr, n, stride, dev = _as_cloud(cloud)
+        keep, ptr, n, stride, dev = self._cloud_args(1, cloud)
         self._check(self.lib.gicpb_set_source(self.h, ptr, n, stride, dev))
 
     def compute_covariances(self):

@@ -165,7 +165,15 @@ struct gicpb_ctx {
   int num_sms = 148;
   size_t l2_persist_bytes = 0, l2_window_max = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // uploads started by gicpb_prefetch_cloud run here, beside the compute stream
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_order = nullptr;
+  struct Prefetch {
+    const void* host = nullptr;
+    int64_t n = 0, stride = 0;
+    unsigned char* dev = nullptr;
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+  } prefetch[2];  // 0 target, 1 source
   gicpb_params prm{};
   std::string err;
 
@@ -547,6 +555,19 @@ void check_cloud_args(const void* p, int64_t n, int64_t stride) {
   if (reinterpret_cast<uintptr_t>(p) % 4) throw ArgError("cloud pointer must be 4-byte aligned");
 }
 
+// true: the host cloud (xyz, n, stride) was uploaded by gicpb_prefetch_cloud; the compute stream now waits for that copy
+bool take_prefetch(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t stride, int on_device) {
+  gicpb_ctx::Prefetch& p = c->prefetch[which];
+  if (!p.pending) return false;
+  p.pending = false;
+  if (on_device || p.host != xyz || p.n != n || p.stride != stride) {
+    GICPB_CUDA(cudaEventSynchronize(p.done));  // a different cloud is being set: let the stale copy finish first
+    return false;
+  }
+  GICPB_CUDA(cudaStreamWaitEvent(c->stream, p.done, 0));
+  return true;
+}
+
 GridIndex& pick_grid(gicpb_ctx* c, int which) {
   if (which == 0) return c->tgt;
   if (which == 1) return c->src;
@@ -598,8 +619,11 @@ int gicpb_create(int device, gicpb_ctx** out) {
     }
     cudaGetLastError();
     GICPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GICPB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     GICPB_CUDA(cudaEventCreate(&c->ev0));
     GICPB_CUDA(cudaEventCreate(&c->ev1));
+    GICPB_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+    for (auto& p : c->prefetch) GICPB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
     GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
     GICPB_CUDA(cudaHostAlloc(&c->h_mom, 80 * sizeof(double), cudaHostAllocDefault));
@@ -626,6 +650,12 @@ void gicpb_destroy(gicpb_ctx* c) {
       if (r != c->rank && c->peer.peers[r]) cudaIpcCloseMemHandle(c->peer.peers[r]);
   if (c->peer_own) cudaFree(c->peer_own);
   if (c->h_far) cudaFreeHost(c->h_far);
+  for (auto& p : c->prefetch) {
+    if (p.pending) cudaEventSynchronize(p.done);
+    if (p.done) cudaEventDestroy(p.done);
+  }
+  if (c->ev_order) cudaEventDestroy(c->ev_order);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -736,11 +766,35 @@ int gicpb_comm_rank(const gicpb_ctx* c, int* rank, int* world) {
   return GICPB_OK;
 }
 
+int gicpb_prefetch_cloud(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t stride) {
+  return guarded(c, [&] {
+    if (which != 0 && which != 1) throw ArgError("which must be 0 (target) or 1 (source)");
+    check_cloud_args(xyz, n, stride);
+    gicpb_ctx::Prefetch& p = c->prefetch[which];
+    if (p.pending) GICPB_CUDA(cudaEventSynchronize(p.done));
+    // the index of this cloud may still be in use on the compute stream (its staging buffer is about to be overwritten)
+    GICPB_CUDA(cudaEventRecord(c->ev_order, c->stream));
+    GICPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
+    GridIndex& g = which == 0 ? c->tgt : c->src;
+    p.dev = g.stage((size_t)n * stride);
+    GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
+    GICPB_CUDA(cudaEventRecord(p.done, c->copy_stream));
+    p.host = xyz;
+    p.n = n;
+    p.stride = stride;
+    p.pending = true;
+  });
+}
+
 int gicpb_set_target(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, int on_device) {
   return guarded(c, [&] {
     check_cloud_args(xyz, n, stride);
     c->cov_ready = false;
     c->pairs_valid = false;
+    if (take_prefetch(c, 0, xyz, n, stride, on_device)) {
+      xyz = c->prefetch[0].dev;
+      on_device = 1;
+    }
     c->tgt.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
   });
 }
@@ -750,6 +804,10 @@ int gicpb_set_source(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, i
     check_cloud_args(xyz, n, stride);
     c->cov_ready = false;
     c->pairs_valid = false;
+    if (take_prefetch(c, 1, xyz, n, stride, on_device)) {
+      xyz = c->prefetch[1].dev;
+      on_device = 1;
+    }
     c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
     update_shard(c);
   });

@@ -85,6 +85,11 @@ class GridIndex {
   int64_t n_points() const { return info_.n_points; }
   const float4* sorted_points() const { return pts_sorted_.get(); }
   void reset() { ready_ = false; }
+  // device staging buffer for a host cloud that the caller uploads itself (prefetch on another stream)
+  unsigned char* stage(size_t bytes) {
+    raw_.reserve(bytes);
+    return raw_.get();
+  }
 
  private:
   bool ready_ = false;

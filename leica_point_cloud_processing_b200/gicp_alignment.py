@@ -158,6 +158,8 @@ class GICPAlignment:
     def _fine_alignment(self):
         # reference :86-109
         log.info("Perform GICP with %d iterations", self.max_iter_)
+        self._engine.prefetch(1, self.source_cloud_)   # both uploads queue on the copy stream, source first:
+        self._engine.prefetch(0, self.target_cloud_)   # the target uploads while the source is indexed
         self._engine.set_source(self.source_cloud_)
         self._engine.set_target(self.target_cloud_)
         self._inputs_set = True
