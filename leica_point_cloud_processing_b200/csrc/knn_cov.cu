@@ -22,8 +22,8 @@ namespace gicpb {
 
 namespace {
 
-constexpr int kKnnThreads = 128;
-using KnnList = KnnVisitor<kKnnThreads>;
+constexpr int kKnnNearThreads = 256;  // consecutive (= neighbouring) queries of one block share its L1 lines
+constexpr int kKnnFarThreads = 128;   // far_for_each needs 128
 
 template <int P, int Q>
 __device__ __forceinline__ void jacobi_rotate(double (&a)[9], double (&v)[9]) {
@@ -56,12 +56,13 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[9], double (&v)[9]) {
 constexpr int kKnnQueueCap = 12;
 
 template <bool kFar>
-__global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
+__global__ void __launch_bounds__(kFar ? kKnnFarThreads : kKnnNearThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
                                                                double* __restrict__ normals,
                                                                int* __restrict__ knn_idx,
                                                                float* __restrict__ knn_d2, FarWork fw) {
   extern __shared__ __align__(8) int smem[];
-  KnnList L;
+  constexpr int kKnnThreads = kFar ? kKnnFarThreads : kKnnNearThreads;
+  KnnVisitor<kKnnThreads> L;
   L.pts = g.pts;
   L.lkey = reinterpret_cast<unsigned long long*>(smem) + threadIdx.x;
   L.k = k;
@@ -157,12 +158,18 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   const int n = hi - lo;
   if (n <= 0) return;
   reset_far(fw, n, stream);
-  const size_t heap = (size_t)2 * k * kKnnThreads * sizeof(int);
-  const size_t queue = (size_t)2 * kKnnQueueCap * kKnnThreads * sizeof(unsigned);
-  const unsigned nb = (unsigned)((n + kKnnThreads - 1) / kKnnThreads);
-  knn_cov_kernel<false><<<nb, kKnnThreads, heap + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
+  const size_t heap_near = (size_t)2 * k * kKnnNearThreads * sizeof(int);
+  const size_t heap = (size_t)2 * k * kKnnFarThreads * sizeof(int);
+  const size_t queue = (size_t)2 * kKnnQueueCap * kKnnNearThreads * sizeof(unsigned);
+  const unsigned nb = (unsigned)((n + kKnnNearThreads - 1) / kKnnNearThreads);
+  static bool attr_set = false;
+  if (!attr_set) {  // 64 KB of dynamic shared memory at k = 32
+    GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  knn_cov_kernel<false><<<nb, kKnnNearThreads, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
   GICPB_LAUNCHED();
-  knn_cov_kernel<true><<<fw.far_blocks, kKnnThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
+  knn_cov_kernel<true><<<fw.far_blocks, kKnnFarThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
   GICPB_LAUNCHED();
 }
 
