@@ -266,6 +266,31 @@ def test_align_fp32_mahalanobis_within_tolerance(engine, oracle, cube_pair):
     assert_transform_close(res["transform"], ref["T"], bbox_diag(src, tgt))
 
 
+def test_prefetched_uploads_give_the_same_result(engine, oracle, cube_pair):
+    """gicpb_prefetch_cloud only moves the upload to a copy stream: same index, same transform; a prefetch that the
+    following set call does not match (another array) is ignored."""
+    src, tgt, _ = cube_pair
+    reset(engine, max_corr_distance=5.0, transformation_epsilon=5e-4)
+    engine.set_target(tgt)
+    engine.set_source(src)
+    plain = engine.align()
+    engine.prefetch(0, tgt)
+    engine.prefetch(1, src)
+    engine.set_target(tgt)
+    engine.set_source(src)
+    pre = engine.align()
+    assert np.array_equal(plain["transform"], pre["transform"])
+    engine.prefetch(1, tgt)                 # stale hint: a different cloud is then set as the source
+    other = src.copy()
+    engine.set_source(other)
+    engine.set_target(tgt)
+    again = engine.align()
+    assert np.array_equal(plain["transform"], again["transform"])
+    idx, d2 = engine.nn1(src)
+    oi, od = oracle.nn1(tgt, src)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+
+
 def test_align_not_enough_correspondences(engine, cube_pair):
     src, tgt, _ = cube_pair
     reset(engine, max_corr_distance=1e-4)
