@@ -39,6 +39,7 @@ namespace gicpb {
 constexpr int kBrickShift = 3;                  // 8 cells per brick edge
 constexpr int kBrickCells = 512;                // 8*8*8
 constexpr int kMaxBoxRows = 81;                 // NN-1: largest (y,z) row count searched as a plain cell box
+constexpr int kSeedBoxRows = 9;                 // NN-1: a seed whose ball spans more rows is first improved by a probe
 constexpr int kNearMaxRing = 3;                // NN-1: cell rings probed for a first candidate before the far search
 constexpr int kKnnMaxRing = 4;                  // kNN: largest cell ring searched before the hierarchical fallback
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -513,7 +514,9 @@ GICPB_HD int nn_near(const GridView& g, const Query& q, NNState& s, unsigned* qb
       const int y0 = imax2(cell_of(fsub(q.y, rad), g.oy, g.inv_h), 0), y1 = imin2(cell_of(fadd(q.y, rad), g.oy, g.inv_h), g.ny - 1);
       const int z0 = imax2(cell_of(fsub(q.z, rad), g.oz, g.inv_h), 0), z1 = imin2(cell_of(fadd(q.z, rad), g.oz, g.inv_h), g.nz - 1);
       if (x0 > x1 || y0 > y1 || z0 > z1) { result = kNear_Done; break; }  // the ball misses the grid: the candidate stands
-      if ((long long)(y1 - y0 + 1) * (z1 - z0 + 1) <= kMaxBoxRows) {
+      // A seed is searched directly only when its ball is small; a mediocre one (a match of a pose that has moved on)
+      // is cheaper to improve first by probing the cells around the query than to scan its whole ball.
+      if ((long long)(y1 - y0 + 1) * (z1 - z0 + 1) <= (probed ? kMaxBoxRows : kSeedBoxRows)) {
         bool stop = visit_box(g, q, x0, x1, y0, y1, z0, z1, qv);
         stop = stop || qv.drain();
         result = stop ? kNear_Stop : kNear_Done;
@@ -536,7 +539,7 @@ GICPB_HD int nn_near(const GridView& g, const Query& q, NNState& s, unsigned* qb
       stop = stop || qv.drain();
     }
     if (stop) { result = kNear_Stop; break; }
-    if (v.s.pos == start_pos) break;  // still nothing closer
+    if (v.s.pos < 0) break;  // nothing nearby at all: the far search takes over
   }
   s = v.s;
   return result;
