@@ -181,7 +181,8 @@ def run_ours(args):
 
     eng = Engine(local_rank)
     fused_peer = init_engine_comm(eng, rank, world)
-    eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32, cost_moments=args.cost_moments)
+    eng.set_params(max_corr_distance=GATE_M, mahalanobis_fp32=args.maha_fp32, cost_moments=args.cost_moments,
+                   use_previous_match=args.seed_previous)
 
     def step(tgt_buf, src_buf):
         # host clouds: both uploads are queued on the copy stream, target first, so that the source uploads while the
@@ -413,6 +414,7 @@ def main():
     ap.add_argument("--ref-points", type=int, default=2_000_000, help="--impl reference sample cap")
     ap.add_argument("--maha-fp32", type=int, default=0)
     ap.add_argument("--cost-moments", type=int, default=0, help="1: the opt-in moments objective (see gicp_b200.h)")
+    ap.add_argument("--seed-previous", type=int, default=1, help="0: do not seed a pass with the previous pass's matches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -39,7 +39,7 @@ namespace gicpb {
 constexpr int kBrickShift = 3;                  // 8 cells per brick edge
 constexpr int kBrickCells = 512;                // 8*8*8
 constexpr int kMaxBoxRows = 81;                 // NN-1: largest (y,z) row count searched as a plain cell box
-constexpr int kSeedBoxRows = 9;                 // NN-1: a seed whose ball spans more rows is first improved by a probe
+constexpr int kSeedBoxRows = 4;                 // NN-1: a seed whose ball spans more rows is first improved by a probe
 constexpr int kNearMaxRing = 3;                // NN-1: cell rings probed for a first candidate before the far search
 constexpr int kKnnMaxRing = 4;                  // kNN: largest cell ring searched before the hierarchical fallback
 constexpr unsigned kFullMask = 0xffffffffu;
