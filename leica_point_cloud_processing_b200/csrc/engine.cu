@@ -1161,6 +1161,7 @@ int gicpb_voxel_grid(gicpb_ctx* c, const void* in, int64_t n, int64_t stride, in
     if (n == 0) return;
     if (!out) throw ArgError("null output");
     check_cloud_args(in, n, stride);
+    if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
     if (!(leaf_size > 0)) throw ArgError("leaf size must be > 0");
     // the last point must reach through its z, and through its rgba word when the stride holds one
     const size_t full = (size_t)n * stride, bytes = (size_t)(n - 1) * stride + (stride >= 20 ? 20 : 12);
