@@ -82,3 +82,59 @@ def test_sharded_sums_reproduce_the_objective(tmp_path, oracle, cube_pair):
         assert out[7] == cnt
         assert abs(out[0] - f) <= 1e-12 * abs(f)
         assert np.allclose(out[1:7], g, rtol=1e-10, atol=1e-13)
+
+
+class _FakeEngine:
+    """Stands in for Engine in the handle exchange of distributed.enable_peer_reduction (no GPU on this box)."""
+
+    def __init__(self, rank, export_fails=False, import_fails=False):
+        self.rank, self.export_fails, self.import_fails = rank, export_fails, import_fails
+        self.imported, self.disabled = None, False
+
+    def peer_export(self):
+        if self.export_fails:
+            raise RuntimeError("no peer access")
+        return bytes([self.rank]) * 64
+
+    def peer_import(self, handles):
+        if self.import_fails:
+            raise RuntimeError("cudaIpcOpenMemHandle failed")
+        self.imported = list(handles)
+
+    def peer_disable(self):
+        self.disabled = True
+
+
+def _peer_worker(rank, world, port, tmpdir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from leica_point_cloud_processing_b200.distributed import enable_peer_reduction
+
+    # every rank can map every other: all enable, and each holds the handles in RANK order
+    ok_all = _FakeEngine(rank)
+    assert enable_peer_reduction(ok_all, rank, world) is True
+    assert ok_all.imported == [bytes([r]) * 64 for r in range(world)] and not ok_all.disabled
+    # one rank cannot export, another cannot import: nobody may use the fused path (a half-enabled job would hang)
+    for kw in (dict(export_fails=(rank == 1)), dict(import_fails=(rank == 0))):
+        eng = _FakeEngine(rank, **kw)
+        assert enable_peer_reduction(eng, rank, world) is False
+        assert eng.disabled
+    # what the last block of the cost kernel does with the slots (cost.cu): sums in rank order on every rank give
+    # bit-identical results everywhere, whichever rank's partials arrived first
+    rng = np.random.default_rng(100 + rank)
+    mine = rng.standard_normal(14) * 10.0 ** rng.integers(-8, 8, 14)
+    slots = [torch.zeros(14, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(slots, torch.from_numpy(mine))
+    total = np.zeros(14)
+    for r in range(world):
+        total += slots[r].numpy()
+    np.save(os.path.join(tmpdir, f"peer{rank}.npy"), total)
+    dist.destroy_process_group()
+
+
+def test_peer_reduction_is_all_or_nothing_and_rank_ordered(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_peer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / "peer0.npy"), np.load(tmp_path / "peer1.npy")
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
