@@ -130,3 +130,36 @@ def test_config4_fod_difference_10M_bit_exact(engine, fast_oracle, pair_10M):
     # idempotence: the kept points, run again, are all kept; the dropped ones are all dropped
     mask2, kept2 = engine.cloud_difference(with_fod[mask.astype(bool)], tgt, thr)
     assert kept2 == kept and mask2.all()
+    # SURVEY 8f row 1 on the same data (src/LeicaStateMachine.cpp:200-205): the kept points cluster into the injected
+    # blobs, label for label as the oracle's restatement of pcl::EuclideanClusterExtraction says
+    diff_cloud = with_fod[mask.astype(bool)]
+    labels, n_clusters = engine.euclidean_clusters(diff_cloud, thr * 100, 3, 0)
+    olab, onc = fast_oracle.euclidean_clusters(diff_cloud, thr * 100, 3, 0)
+    assert n_clusters == onc and 1 <= n_clusters <= 20
+    assert np.array_equal(labels, olab)
+
+
+def test_voxel_grid_10M_bit_exact(engine, fast_oracle, pair_10M):
+    """SURVEY 8f row 3 at the size of config 3: Filter::downsampleCloud of the 10 M-point scan as PointXYZRGB rows with
+    the leaf the pipeline uses (10 x cloud resolution, src/LeicaStateMachine.cpp:61-65); centroids bit for bit, and
+    the size-independent properties: every point lands in exactly one voxel, centroids lie inside their voxel."""
+    src, _, _ = pair_10M
+    rng = np.random.default_rng(3)
+    cloud = np.zeros((len(src), 8), np.float32)
+    cloud[:, :3] = src
+    cloud[:, 3] = 1.0
+    cloud[:, 4] = rng.integers(0, 2 ** 32, len(src), dtype=np.uint64).astype(np.uint32).view(np.float32)
+    engine.set_target(src)
+    leaf = np.float32(10.0 * engine.cloud_resolution(0))
+    t0 = time.perf_counter()
+    out = engine.voxel_grid(cloud, leaf)
+    dt = time.perf_counter() - t0
+    print(f"voxel grid {len(cloud)} -> {len(out)} points, leaf {float(leaf) * 1e3:.1f} mm: {dt * 1e3:.1f} ms from host clouds")
+    ref = fast_oracle.voxel_grid(cloud, leaf)
+    assert out.shape == ref.shape
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    inv = np.float32(1.0) / leaf
+    vox = np.floor(out[:, :3] * inv).astype(np.int64)
+    assert len(np.unique(vox, axis=0)) == len(out)            # one centroid per voxel, each inside its own voxel
+    assert np.all(np.diff(((vox - vox.min(0)) * [1, (vox[:, 0].max() - vox[:, 0].min() + 1),
+                                                  (vox[:, 0].max() - vox[:, 0].min() + 1) * (vox[:, 1].max() - vox[:, 1].min() + 1)]).sum(1)) > 0)
