@@ -10,8 +10,11 @@ kNN-20 covariances, the GICP outer loop to convergence, fitness score.  `value` 
 already resident in HBM; `e2e` goes through the same C-ABI calls with pinned HOST buffers, so the host->device copy
 of both clouds and the read-back of the transform and fitness are inside the timed region.
 value = (source queries answered by the correspondence kernel over all outer iterations, all ranks) / step time.
-N > 1: source sharded by rank (weak scaling: 1 M source AND target points per GPU), target replicated, one NCCL
-all-reduce of 14 doubles per cost evaluation.
+N > 1: source sharded by rank (weak scaling: 1 M source AND target points per GPU), target replicated; the 14 partial
+sums of a cost evaluation are added across the GPUs inside the cost kernel over NVLink peer memory (ncclAllReduce when
+the ranks cannot map each other's memory).
+detail.* holds secondary measurements taken outside the timed steps: per-kernel times, the opt-in moments objective,
+and the FOD pipeline rows either side of the registration (cloud difference, Euclidean clusters, voxel grid).
 """
 import argparse
 import json
