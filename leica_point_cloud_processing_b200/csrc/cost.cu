@@ -15,8 +15,9 @@ namespace gicpb {
 
 namespace {
 
-constexpr int kCostThreads = 512;
+constexpr int kCostThreads = 256;          // one pair per thread and tile
 constexpr int kCostWarps = kCostThreads / 32;
+constexpr int kCostStages = 2;             // shared-memory ring: 2 x 256 pairs x 80 B = 40 KB per CTA, 2 CTAs per SM
 
 template <typename MT>
 struct PairData {
@@ -37,6 +38,24 @@ __device__ __forceinline__ void load_pair(const float4* __restrict__ src, const 
   } else {                // 24 B per pair, 8-byte aligned: three 64-bit loads
     const float2* m2 = reinterpret_cast<const float2*>(m);
     const float2 a = __ldg(m2), b = __ldg(m2 + 1), c = __ldg(m2 + 2);
+    d.m[0] = (MT)a.x; d.m[1] = (MT)a.y; d.m[2] = (MT)b.x; d.m[3] = (MT)b.y; d.m[4] = (MT)c.x; d.m[5] = (MT)c.y;
+  }
+}
+
+// the same pair out of a shared-memory stage (rows of 16 / 16 / 6*sizeof(MT) bytes; 128-bit reads of the 48-byte M rows
+// are conflict-free: the 8 lanes of a quarter warp start at banks 0 12 24 4 16 28 8 20)
+template <typename MT>
+__device__ __forceinline__ void load_pair_smem(const unsigned char* stage, int i, PairData<MT>& d) {
+  d.q = *reinterpret_cast<const float4*>(stage + i * 16);
+  d.p = *reinterpret_cast<const float4*>(stage + kCostThreads * 16 + i * 16);
+  const unsigned char* m = stage + kCostThreads * 32 + i * (6 * (int)sizeof(MT));
+  if (sizeof(MT) == 8) {
+    const double2* m2 = reinterpret_cast<const double2*>(m);
+    const double2 a = m2[0], b = m2[1], c = m2[2];
+    d.m[0] = (MT)a.x; d.m[1] = (MT)a.y; d.m[2] = (MT)b.x; d.m[3] = (MT)b.y; d.m[4] = (MT)c.x; d.m[5] = (MT)c.y;
+  } else {
+    const float2* m2 = reinterpret_cast<const float2*>(m);
+    const float2 a = m2[0], b = m2[1], c = m2[2];
     d.m[0] = (MT)a.x; d.m[1] = (MT)a.y; d.m[2] = (MT)b.x; d.m[3] = (MT)b.y; d.m[4] = (MT)c.x; d.m[5] = (MT)c.y;
   }
 }
@@ -64,27 +83,89 @@ __device__ __forceinline__ void add_pair(const PairData<MT>& d, const Rigid& T, 
   acc[13] += 1.0;
 }
 
+// ---- bulk asynchronous copies (TMA, 1-D) into shared memory, completion counted in bytes on an mbarrier -------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Tiles of 256 consecutive pairs are three contiguous spans in global memory (pair_tgt, src, maha).  One elected thread
+// streams them into a two-stage shared-memory ring with cp.async.bulk (TMA): the loads of the next tile are in flight
+// while the block reduces the current one, no thread holds a second pair in registers (the former register
+// double-buffer spilled at 64 registers and, at 10 M pairs, ran at half the bandwidth of this kernel:
+// scripts/micro/cost_variants.cu).  A last partial tile is read with plain loads (its byte count need not be a
+// multiple of 16).
 template <typename MT, bool kPeer>
-__global__ void __launch_bounds__(kCostThreads, 2) cost_kernel(const float4* __restrict__ src, int lo, int n,
-                                                                const float4* __restrict__ pair_tgt,
-                                                                const MT* __restrict__ maha, Rigid T,
-                                                                double* __restrict__ partials, unsigned* __restrict__ ticket,
-                                                                double* __restrict__ out, PeerReduce pr) {
+__global__ void __launch_bounds__(kCostThreads) cost_kernel(const float4* __restrict__ src, int lo, int n,
+                                                             const float4* __restrict__ pair_tgt,
+                                                             const MT* __restrict__ maha, Rigid T,
+                                                             double* __restrict__ partials, unsigned* __restrict__ ticket,
+                                                             double* __restrict__ out, PeerReduce pr) {
+  constexpr int kRowM = 6 * (int)sizeof(MT);
+  constexpr int kStageBytes = kCostThreads * (32 + kRowM);
+  __shared__ __align__(128) unsigned char ring[kCostStages * kStageBytes];
+  __shared__ __align__(8) unsigned long long full[kCostStages];
   double acc[kCostSums];
 #pragma unroll
   for (int c = 0; c < kCostSums; ++c) acc[c] = 0.0;
 
-  // two pairs in flight per thread: the loads of the next pair are issued before the current one is reduced
-  const int stride = gridDim.x * kCostThreads;
-  int t = blockIdx.x * kCostThreads + threadIdx.x;
-  PairData<MT> cur, nxt;
-  if (t < n) load_pair(src, pair_tgt, maha, lo, t, cur);
-  while (t < n) {
-    const int tn = t + stride;
-    if (tn < n) load_pair(src, pair_tgt, maha, lo, tn, nxt);
-    add_pair(cur, T, acc);
-    cur = nxt;
-    t = tn;
+  const int full_tiles = n / kCostThreads;
+  auto issue = [&](int tile, int s) {
+    const size_t t0 = (size_t)tile * kCostThreads;
+    unsigned char* stage = ring + s * kStageBytes;
+    mbar_expect_tx(&full[s], kStageBytes);
+    bulk_g2s(stage, pair_tgt + t0, kCostThreads * 16, &full[s]);
+    bulk_g2s(stage + kCostThreads * 16, src + lo + t0, kCostThreads * 16, &full[s]);
+    bulk_g2s(stage + kCostThreads * 32, maha + 6 * t0, kCostThreads * kRowM, &full[s]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kCostStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kCostStages; ++s) {
+      const int tile = blockIdx.x + s * gridDim.x;
+      if (tile < full_tiles) issue(tile, s);
+    }
+  }
+  int k = 0;
+  for (int tile = blockIdx.x; tile < full_tiles; tile += gridDim.x, ++k) {
+    const int s = k % kCostStages;
+    mbar_wait(&full[s], (unsigned)(k / kCostStages) & 1u);
+    PairData<MT> d;
+    load_pair_smem<MT>(ring + s * kStageBytes, threadIdx.x, d);
+    add_pair(d, T, acc);
+    __syncthreads();  // every thread has read stage s: it may be refilled
+    if (threadIdx.x == 0) {
+      const int nt = tile + kCostStages * gridDim.x;
+      if (nt < full_tiles) issue(nt, s);
+    }
+  }
+  if ((int)blockIdx.x == full_tiles % (int)gridDim.x) {  // the partial tile, if any, goes to the next block in turn
+    const int t = full_tiles * kCostThreads + threadIdx.x;
+    if (t < n) {
+      PairData<MT> d;
+      load_pair(src, pair_tgt, maha, lo, t, d);
+      add_pair(d, T, acc);
+    }
   }
 
   __shared__ double sm[kCostWarps][kCostSums + 2];
@@ -112,7 +193,7 @@ __global__ void __launch_bounds__(kCostThreads, 2) cost_kernel(const float4* __r
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // last block: column c = thread & 15, row group = thread >> 4 (32 groups); every thread sums its rows of the
+  // last block: column c = thread & 15, row group = thread >> 4 (16 groups); every thread sums its rows of the
   // per-block partials (rows are 16 doubles apart: one 128-byte line per row), then the groups are added in a
   // fixed order - a given input always produces the same bits
   const int c = threadIdx.x & 15, grp = threadIdx.x >> 4;
@@ -278,7 +359,7 @@ __global__ void __launch_bounds__(kMomThreads, 1) moments_kernel(const float4* _
 
 int cost_grid_blocks(int n, int num_sms) {
   const int want = (n + kCostThreads - 1) / kCostThreads;
-  const int cap = num_sms * 2;  // a multiple of the SM count; 2 resident CTAs of 512 threads per SM
+  const int cap = num_sms * 2;  // a multiple of the SM count; 2 resident CTAs (40 KB of staging each) per SM
   return std::max(1, std::min(want, cap));
 }
 
