@@ -342,6 +342,11 @@ def run_ours(args):
         eng.set_target(d_tgt)
         ms_vox, vox = dev_ms(lambda: eng.voxel_grid(rgb, leaf))
         n_fod = int(d_fod.shape[0])
+        # the node's input (src/node.cpp:37): a PointCloud2 payload as pcl::toROSMsg lays it out, gathered into rows
+        msg = rgb.view(torch.uint8).reshape(-1)
+        ms_pc2, _ = dev_ms(lambda: eng.pointcloud2_to_xyzrgb(msg, n, 1, 32, 32 * n, 0, 4, 8, 16, device_out=True))
+        extra["pointcloud2_unpack"] = dict(kern(ms_pc2, 64.0 * n), points=n,
+                                           includes="output allocation by torch + the gather kernel; 32 B in + 32 B out per point")
         extra["fod_pipeline"] = {
             "cloud_difference": dict(kern(ms_diff, 16.0 * n_fod + 16.0 * n + n_fod), points_in=n_fod, kept=int(kept),
                                      includes="index build of the subtract cloud + difference kernels"),

@@ -167,6 +167,41 @@ int gicpb_euclidean_clusters(gicpb_ctx* ctx, const void* cloud, int64_t n, int64
 int gicpb_voxel_grid(gicpb_ctx* ctx, const void* in, int64_t n, int64_t stride_bytes, int on_device, double leaf_size,
                      void* out, int64_t* n_out);
 
+/* ---- the wire and on-disk formats at the boundary ------------------------------------------
+ * pcl::fromROSMsg(sensor_msgs::PointCloud2, pcl::PointCloud<pcl::PointXYZRGB>) (src/node.cpp:37,41, the two clouds the
+ * node receives): the caller looks the fields up by name (pcl::FieldMatches: x, y, z FLOAT32 count 1; "rgb" FLOAT32 or
+ * "rgba" UINT32) and passes their byte offsets; the GPU gathers them into 32-byte pcl::PointXYZRGB rows
+ * (x, y, z, 1.0f, rgba word, 12 zero bytes) in `points32` (width * height rows, host or device).  off_rgb < 0: the
+ * message has no colour field, every point keeps PointXYZRGB()'s default (r = g = b = 0, a = 255).  is_bigendian is
+ * ignored, as PCL ignores it.  A message whose x, y, z are consecutive floats needs no unpacking at all:
+ * gicpb_set_source(ctx, data + off_x, n, point_step, ...) reads it in place.
+ * The reverse, pcl::toROSMsg (Utils::cloudToROSMsg, src/Utils.cpp:100-105), is a plain copy of the 32-byte rows: the
+ * message is fields x@0 y@4 z@8 rgb@16 (FLOAT32, count 1), point_step 32, row_step 32 * width. */
+typedef struct gicpb_pc2_layout {
+  int64_t width, height;      /* points = width * height                                                   */
+  int64_t point_step;         /* bytes between points of a row                                             */
+  int64_t row_step;           /* bytes between rows (>= width * point_step)                                */
+  int32_t off_x, off_y, off_z; /* byte offsets of the FLOAT32 fields inside a point                        */
+  int32_t off_rgb;            /* byte offset of the 4-byte rgb / rgba field, < 0: none                     */
+} gicpb_pc2_layout;
+int gicpb_pointcloud2_to_xyzrgb(gicpb_ctx* ctx, const void* data, int data_on_device, const gicpb_pc2_layout* layout,
+                                void* points32, int points_on_device);
+
+/* pcl::io::loadPCDFile<pcl::PointXYZRGB> (src/load_and_publish_clouds.cpp:75): PCL 1.8.1's PCDReader (header v0.7,
+ * DATA ascii / binary / binary_compressed) read on the host into the PointCloud2-style blob, fields mapped to
+ * PointXYZRGB rows on the GPU as above.  points32 == NULL: only the header is read (info->points tells the caller how
+ * many 32-byte rows to provide); otherwise `capacity` rows must be >= info->points. */
+typedef struct gicpb_pcd_info {
+  int64_t width, height, points;
+  int32_t point_step;          /* bytes per point in the file's own layout                                  */
+  int32_t n_fields;
+  int32_t data_kind;           /* 0 ascii, 1 binary, 2 binary_compressed                                    */
+  int32_t is_dense;            /* 0 if the body holds a NaN / Inf (only known after the body was read)      */
+  int32_t off_x, off_y, off_z, off_rgb; /* where PointXYZRGB's fields sit in the file's layout, -1: absent  */
+} gicpb_pcd_info;
+int gicpb_pcd_load_xyzrgb(gicpb_ctx* ctx, const char* path, void* points32, int64_t capacity, int points_on_device,
+                          gicpb_pcd_info* info);
+
 /* ---- test / inspection hooks (parity checks against the oracle) ------------------------------------- */
 /* exact NN-1 of `n` queries in the target: idx = ORIGINAL target index (-1: none), d2 = float32 squared
  * distance.  max_dist <= 0 -> ungated; else only neighbours with d2 < max_dist^2 (strict) are reported. */

@@ -69,6 +69,36 @@ class GridInfo(ctypes.Structure):
     ]
 
 
+class Pc2Layout(ctypes.Structure):
+    """gicpb_pc2_layout: where a sensor_msgs/PointCloud2 payload keeps the fields a pcl::PointXYZRGB maps."""
+    _fields_ = [
+        ("width", ctypes.c_int64),
+        ("height", ctypes.c_int64),
+        ("point_step", ctypes.c_int64),
+        ("row_step", ctypes.c_int64),
+        ("off_x", ctypes.c_int32),
+        ("off_y", ctypes.c_int32),
+        ("off_z", ctypes.c_int32),
+        ("off_rgb", ctypes.c_int32),
+    ]
+
+
+class PcdInfo(ctypes.Structure):
+    _fields_ = [
+        ("width", ctypes.c_int64),
+        ("height", ctypes.c_int64),
+        ("points", ctypes.c_int64),
+        ("point_step", ctypes.c_int32),
+        ("n_fields", ctypes.c_int32),
+        ("data_kind", ctypes.c_int32),
+        ("is_dense", ctypes.c_int32),
+        ("off_x", ctypes.c_int32),
+        ("off_y", ctypes.c_int32),
+        ("off_z", ctypes.c_int32),
+        ("off_rgb", ctypes.c_int32),
+    ]
+
+
 # every symbol include/gicp_b200.h declares: (name, restype, argtypes)
 _VOID_P = ctypes.c_void_p
 _SIGNATURES = [
@@ -111,6 +141,10 @@ _SIGNATURES = [
                                                 ctypes.c_double, ctypes.c_int64, ctypes.c_int64, c_int32_p, c_int64_p]),
     ("gicpb_voxel_grid", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
                                         _VOID_P, c_int64_p]),
+    ("gicpb_pointcloud2_to_xyzrgb", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int, ctypes.POINTER(Pc2Layout), _VOID_P,
+                                                   ctypes.c_int]),
+    ("gicpb_pcd_load_xyzrgb", ctypes.c_int, [_VOID_P, ctypes.c_char_p, _VOID_P, ctypes.c_int64, ctypes.c_int,
+                                             ctypes.POINTER(PcdInfo)]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
     ("gicpb_stream", ctypes.c_void_p, [_VOID_P]),
     ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
@@ -376,6 +410,51 @@ class Engine:
             optr = out.ctypes.data
         self._check(self.lib.gicpb_voxel_grid(self.h, ptr, n, stride, dev, float(leaf_size), optr, ctypes.byref(m)))
         return out[: int(m.value)]
+
+    # ---- wire / on-disk formats -------------------------------------------------------
+    def pointcloud2_to_xyzrgb(self, data, width, height, point_step, row_step, off_x, off_y, off_z, off_rgb=-1,
+                              device_out=False):
+        """pcl::fromROSMsg into pcl::PointXYZRGB rows: float32 [width * height, 8] (x, y, z, 1, rgba bits, 0, 0, 0).
+        `data`: the message payload (bytes / uint8 array, or a CUDA uint8 tensor)."""
+        n = int(width) * int(height)
+        lay = Pc2Layout(int(width), int(height), int(point_step), int(row_step), int(off_x), int(off_y), int(off_z),
+                        int(off_rgb))
+        if hasattr(data, "is_cuda"):
+            dptr, ddev, keep = data.data_ptr(), 1 if data.is_cuda else 0, data
+        else:
+            keep = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data).view(np.uint8)
+            dptr, ddev = keep.ctypes.data, 0
+        if device_out:
+            import torch
+            out = torch.empty((n, 8), dtype=torch.float32, device=f"cuda:{self.device}")
+            optr, odev = out.data_ptr(), 1
+        else:
+            out = np.empty((n, 8), np.float32)
+            optr, odev = out.ctypes.data, 0
+        self._check(self.lib.gicpb_pointcloud2_to_xyzrgb(self.h, dptr if n else None, ddev, ctypes.byref(lay), optr if n else None, odev))
+        return out
+
+    def pcd_info(self, path):
+        """Header of a PCD file (pcl::PCDReader::readHeader) as a dict."""
+        info = PcdInfo()
+        self._check(self.lib.gicpb_pcd_load_xyzrgb(self.h, os.fsencode(path), None, 0, 0, ctypes.byref(info)))
+        return {k: int(getattr(info, k)) for k, _ in PcdInfo._fields_}
+
+    def load_pcd(self, path, device_out=False):
+        """pcl::io::loadPCDFile<pcl::PointXYZRGB>: (float32 [points, 8] rows as pointcloud2_to_xyzrgb, info dict)."""
+        n = self.pcd_info(path)["points"]
+        if device_out:
+            import torch
+            out = torch.empty((n, 8), dtype=torch.float32, device=f"cuda:{self.device}")
+            optr, odev = out.data_ptr(), 1
+        else:
+            out = np.empty((n, 8), np.float32)
+            optr, odev = out.ctypes.data, 0
+        info = PcdInfo()
+        # a dummy non-null pointer for an empty file: the call must still read the body section
+        self._check(self.lib.gicpb_pcd_load_xyzrgb(self.h, os.fsencode(path), optr if n else ctypes.addressof(info), n, odev,
+                                                   ctypes.byref(info)))
+        return out, {k: int(getattr(info, k)) for k, _ in PcdInfo._fields_}
 
     # ---- hooks ----------------------------------------------------------------------------------------
     def nn1(self, queries, T=None, max_dist=0.0):

@@ -15,6 +15,7 @@
 #include <memory>
 
 #include "../../include/gicp_b200.h"
+#include "cloud_io.hpp"
 #include "kernels.hpp"
 #include "optimizer.hpp"
 
@@ -1193,6 +1194,87 @@ int gicpb_voxel_grid(gicpb_ctx* c, const void* in, int64_t n, int64_t stride, in
                                  c->stream));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
     *n_out = m;
+  });
+}
+
+// ---- PointCloud2 payloads and PCD files -> pcl::PointXYZRGB rows ------------------------------------------
+namespace {
+void unpack_pc2(gicpb_ctx* c, const void* data, bool data_on_device, const gicpb_pc2_layout& L, void* points32,
+                bool points_on_device) {
+  if (L.width < 0 || L.height < 0) throw ArgError("negative width / height");
+  const int64_t n = L.width * L.height;
+  if (n == 0) return;
+  if (!data || !points32) throw ArgError("null pointer");
+  if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
+  if (L.point_step < 12 || L.row_step < L.width * L.point_step) throw ArgError("point_step / row_step too small");
+  const int32_t offs[3] = {L.off_x, L.off_y, L.off_z};
+  for (int32_t o : offs)
+    if (o < 0 || (int64_t)o + 4 > L.point_step) throw ArgError("x / y / z offset outside the point");
+  if (L.off_rgb >= 0 && (int64_t)L.off_rgb + 4 > L.point_step) throw ArgError("rgb offset outside the point");
+  const size_t in_bytes = (size_t)(L.height - 1) * L.row_step + (size_t)L.width * L.point_step;
+  const unsigned char* d_in = static_cast<const unsigned char*>(data);
+  if (!data_on_device) {
+    c->io_a.reserve(in_bytes);
+    GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), data, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    d_in = c->io_a.get();
+  }
+  float4* d_out = static_cast<float4*>(points32);
+  if (!points_on_device) {
+    c->io_b.reserve((size_t)n * 32);
+    d_out = reinterpret_cast<float4*>(c->io_b.get());
+  } else if (reinterpret_cast<uintptr_t>(points32) % 16) {
+    throw ArgError("device output must be 16-byte aligned");
+  }
+  launch_pc2_unpack(d_in, n, L.width, L.point_step, L.row_step, L.off_x, L.off_y, L.off_z, L.off_rgb, d_out, c->stream);
+  if (!points_on_device) GICPB_CUDA(cudaMemcpyAsync(points32, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+}
+}  // namespace
+
+int gicpb_pointcloud2_to_xyzrgb(gicpb_ctx* c, const void* data, int data_on_device, const gicpb_pc2_layout* layout,
+                                void* points32, int points_on_device) {
+  return guarded(c, [&] {
+    if (!layout) throw ArgError("null layout");
+    unpack_pc2(c, data, data_on_device != 0, *layout, points32, points_on_device != 0);
+  });
+}
+
+int gicpb_pcd_load_xyzrgb(gicpb_ctx* c, const char* path, void* points32, int64_t capacity, int points_on_device,
+                          gicpb_pcd_info* info) {
+  return guarded(c, [&] {
+    if (!path || !info) throw ArgError("null path / info");
+    PcdFile f;
+    f.read_header(path);
+    std::memset(info, 0, sizeof(*info));
+    info->width = f.width;
+    info->height = f.height;
+    info->points = f.points;
+    info->point_step = f.point_step;
+    info->n_fields = (int32_t)f.fields.size();
+    info->data_kind = f.data_kind;
+    info->is_dense = 1;
+    info->off_x = f.off_x;
+    info->off_y = f.off_y;
+    info->off_z = f.off_z;
+    info->off_rgb = f.off_rgb;
+    if (!points32) return;  // header only
+    if (capacity < f.points) throw ArgError("output holds fewer rows than the file has points");
+    if (f.off_x < 0 || f.off_y < 0 || f.off_z < 0) throw ArgError("PCD file has no FLOAT32 x / y / z fields");
+    if (f.points == 0) return;
+    // the body lands in pinned memory so that the upload is one asynchronous copy
+    const size_t bytes = (size_t)f.points * f.point_step;
+    unsigned char* blob = nullptr;
+    GICPB_CUDA(cudaMallocHost(&blob, bytes));
+    try {
+      f.read_body(path, blob);
+      info->is_dense = f.is_dense ? 1 : 0;
+      gicpb_pc2_layout L{f.points, 1, f.point_step, f.points * (int64_t)f.point_step, f.off_x, f.off_y, f.off_z, f.off_rgb};
+      unpack_pc2(c, blob, false, L, points32, points_on_device != 0);
+    } catch (...) {
+      cudaFreeHost(blob);
+      throw;
+    }
+    cudaFreeHost(blob);
   });
 }
 

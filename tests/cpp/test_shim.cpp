@@ -5,10 +5,12 @@
 // Prints one "RESULT key value..." line per check; exit code 0 iff every check passed.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <type_traits>
 
+#include "CloudIO_b200.hpp"
 #include "FODDetector_b200.hpp"
 #include "GICPAlignment_b200.hpp"
 
@@ -212,6 +214,40 @@ int main(int argc, char** argv) {
     EXPECT_TRUE(!down->points.empty() && down->points.size() < cloudRGB->points.size());
     EXPECT_TRUE(down->points[0].r == 255 && down->points[0].a == 255 && down->points[0].w == 1.f && down->is_dense);
   }
+  {  // node.cpp:37 fromROSMsg, Utils.cpp:102 toROSMsg, load_and_publish_clouds.cpp:75 loadPCDFile
+    gicpb_shim::PointCloud2 msg;
+    gicpb_shim::toROSMsg(*sourceRGB, msg);
+    EXPECT_TRUE(msg.point_step == 32 && msg.width == sourceRGB->points.size() && msg.height == 1);
+    EXPECT_TRUE(msg.fields.size() == 4 && msg.fields[3].name == "rgb" && msg.fields[3].offset == 16);
+    PointCloudRGB back;
+    gicpb_shim::fromROSMsg(msg, back);
+    bool same = back.points.size() == sourceRGB->points.size();
+    for (size_t i = 0; same && i < back.points.size(); ++i)
+      same = std::memcmp(&back.points[i], &sourceRGB->points[i], 20) == 0 && back.points[i].w == 1.f;
+    EXPECT_TRUE(same);
+    // a message of another driver: intensity first, no colour -> default colour (a = 255)
+    gicpb_shim::PointCloud2 other;
+    other.width = 3; other.height = 1; other.point_step = 16; other.row_step = 48;
+    const char* nm[4] = {"intensity", "x", "y", "z"};
+    for (int i = 0; i < 4; ++i) { gicpb_shim::PointField f; f.name = nm[i]; f.offset = 4u * i; f.datatype = gicpb_shim::kFLOAT32; other.fields.push_back(f); }
+    const float vals[12] = {9, 1, 2, 3, 9, 4, 5, 6, 9, 7, 8, 10};
+    other.data.assign(reinterpret_cast<const uint8_t*>(vals), reinterpret_cast<const uint8_t*>(vals) + 48);
+    PointCloudRGB o;
+    gicpb_shim::fromROSMsg(other, o);
+    EXPECT_TRUE(o.points.size() == 3 && o.points[2].x == 7.f && o.points[2].z == 10.f && o.points[1].y == 5.f);
+    EXPECT_TRUE(o.points[0].a == 255 && o.points[0].r == 0 && o.points[0].w == 1.f);
+    if (argc > 3) {  // a binary PCD file of the source cloud written by the test driver
+      PointCloudRGB pc;
+      EXPECT_TRUE(gicpb_shim::loadPCDFile(argv[3], pc) == 0);
+      bool eq = pc.points.size() == sourceRGB->points.size();
+      for (size_t i = 0; eq && i < pc.points.size(); ++i)
+        eq = pc.points[i].x == sourceRGB->points[i].x && pc.points[i].y == sourceRGB->points[i].y && pc.points[i].z == sourceRGB->points[i].z;
+      EXPECT_TRUE(eq);
+      EXPECT_TRUE(gicpb_shim::loadPCDFile(std::string(argv[3]) + ".missing", pc) == -1);
+      std::printf("RESULT pcd_points %zu\n", pc.points.size());
+    }
+  }
+
   std::printf("RESULT failed %d\n", g_failed);
   return g_failed ? 1 : 0;
 }

@@ -24,7 +24,8 @@ def test_shim_compiles_and_links(tmp_path):
     exe = build(tmp_path)
     out = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
     for sym in ("gicpb_create", "gicpb_align", "gicpb_set_source", "gicpb_set_target", "gicpb_fitness",
-                "gicpb_transform_cloud", "gicpb_cloud_difference", "gicpb_euclidean_clusters", "gicpb_voxel_grid"):
+                "gicpb_transform_cloud", "gicpb_cloud_difference", "gicpb_euclidean_clusters", "gicpb_voxel_grid",
+                "gicpb_pointcloud2_to_xyzrgb", "gicpb_pcd_load_xyzrgb"):
         assert sym in out
     # the reference's public surface is all there (include/GICPAlignment.h:47-145)
     hdr = open(os.path.join(ROOT, "include", "GICPAlignment_b200.hpp")).read()
@@ -43,9 +44,13 @@ def test_reference_gtests_through_the_cpp_shim(tmp_path, cube_pair, oracle):
     src, tgt, T = cube_pair
     src.astype(np.float32).tofile(str(tmp_path / "source.f32"))
     tgt.astype(np.float32).tofile(str(tmp_path / "target.f32"))
+    from oracle import cloud_io as oio
+    s32 = src.astype(np.float32)
+    oio.pcd_write(str(tmp_path / "source.pcd"), [("x", 4, "F", 1), ("y", 4, "F", 1), ("z", 4, "F", 1)],
+                  [s32[:, 0], s32[:, 1], s32[:, 2]], "binary_compressed")
     exe = build(tmp_path)
-    run = subprocess.run([exe, str(tmp_path / "source.f32"), str(tmp_path / "target.f32")], capture_output=True, text=True,
-                         timeout=600)
+    run = subprocess.run([exe, str(tmp_path / "source.f32"), str(tmp_path / "target.f32"), str(tmp_path / "source.pcd")],
+                         capture_output=True, text=True, timeout=600)
     print(run.stdout[-4000:], run.stderr[-2000:])
     assert run.returncode == 0
     res = {}
@@ -54,6 +59,7 @@ def test_reference_gtests_through_the_cpp_shim(tmp_path, cube_pair, oracle):
             parts = line.split()
             res[parts[1]] = parts[2:]
     assert res["failed"] == ["0"]
+    assert res["pcd_points"] == [str(len(src))]  # loadPCDFile (src/load_and_publish_clouds.cpp:75) through the shim
     assert res["fod_clusters"][0] == "3"      # test/test_fod_detector.cpp:70 ASSERT_EQ(num_of_fods, 3)
     # testRun parameters (gate 5, tf_eps 5e-4): same transform as the oracle, inside the north_star tolerances
     T_gpu = np.array([float(v) for v in res["run_transform"]]).reshape(4, 4)
