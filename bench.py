@@ -144,7 +144,7 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": "correspondences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -405,13 +405,31 @@ def run_ours(args):
             "clocks": clocks,
             "detail": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else this process or its libraries print
+    (NCCL's version banner, torchrun notes) has been sent to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # fd 1 now points at stderr: stdout carries nothing but the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
