@@ -27,6 +27,7 @@ rgb = np.zeros((n, 8), np.float32)
 rgb[:, :3] = src
 rgb[:, 3] = 1.0
 vox = eng.voxel_grid(rgb, 0.0185)
+rows = eng.pointcloud2_to_xyzrgb(rgb, n, 1, 32, 32 * n, 0, 4, 8, 16)
 eng.set_params(cost_moments=1)                                                          # the opt-in objective
 res_m = eng.align()
 eng.set_params(cost_moments=0)
