@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cmath>
@@ -198,6 +199,7 @@ struct gicpb_ctx {
   double* h_mom = nullptr;        // pinned: the 74 moment sums of the current outer iteration (all ranks)
   float mom_T0[16];               // the transform the moments were taken around
   bool mom_valid = false;
+  unsigned eval_stamp = 0;        // last stamp handed to a cost kernel (run_cost polls for it)
   double* h_sums = nullptr;       // pinned, mapped
   double* h_sums_dev = nullptr;   // device alias of h_sums
   unsigned* h_far = nullptr;      // pinned: far-query count of the last correspondence pass
@@ -417,14 +419,37 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
   if (fused) {
     if (++c->peer.seq == 0u) c->peer.seq = 1u;
   }
+  // the sums land in mapped host memory: the host polls the stamp the kernel stores after them (no driver call between
+  // the kernel's last store and the optimiser's next step); the NCCL path still synchronises the stream
+  const bool polled = out == c->h_sums_dev;
+  unsigned stamp = 0;
+  if (polled) {
+    if (++c->eval_stamp == 0u || c->eval_stamp >= (1u << 30)) c->eval_stamp = 1u;
+    stamp = c->eval_stamp;
+  }
   launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32, T,
-              c->partials.get(), c->ticket.get(), out, blocks, c->stream, fused ? &c->peer : nullptr);
-  if (c->world > 1 && !fused) {
+              c->partials.get(), c->ticket.get(), out, blocks, c->stream, fused ? &c->peer : nullptr, stamp);
+  if (polled) {
+    const volatile double* flag = c->h_sums + 15;
+    const double want = (double)stamp;
+    for (unsigned spins = 1; *flag != want; ++spins) {
+      if ((spins & 0x3fffu) == 0u) {  // every ~16 k polls: has the kernel died, or finished without publishing?
+        const cudaError_t q = cudaStreamQuery(c->stream);
+        if (q == cudaSuccess) {
+          if (*flag == want) break;
+          throw CudaError("cost kernel finished without publishing its sums");
+        }
+        if (q != cudaErrorNotReady) GICPB_CUDA(q);
+        (void)cudaGetLastError();
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  } else {
     all_reduce_sum(c, c->d_sums.get(), kCostSums);
     GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), kCostSums * sizeof(double), cudaMemcpyDeviceToHost,
                                c->stream));
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
   }
-  GICPB_CUDA(cudaStreamSynchronize(c->stream));
   for (int i = 0; i < kCostSums; ++i) sums[i] = c->h_sums[i];
   if (fused && std::isnan(sums[13])) throw NcclError("peer-memory reduction timed out: a rank did not launch this evaluation");
   ++c->cost_evals;
@@ -482,7 +507,9 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
       if (first_eval) {
         first_eval = false;
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->ms_corr += ms;
+        // run_cost may have polled instead of synchronising: the kernel it waited for ran after ev1 on this stream
+        if (cudaEventSynchronize(c->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess)
+          c->ms_corr += ms;
         c->far_queries += c->h_far[0];
       }
       m_pairs = s[13];
@@ -833,7 +860,9 @@ int gicpb_fitness(gicpb_ctx* c, const float transform[16], double max_range, dou
     ensure_pair_buffers(c);
     const Rigid T = rigid_from_rowmajor(transform);
     double* partials = c->partials.get() + (size_t)c->num_sms * 4 * 16;
-    launch_fitness(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, max_range, partials,
+    // the matches of the last correspondence pass (same clouds, a nearby pose) seed the search
+    const int* seed = (c->prm.use_previous_match != 0 && c->pairs_valid) ? c->pair_pos.get() : nullptr;
+    launch_fitness(c->tgt.view(), c->src.sorted_points(), c->shard_lo, c->shard_hi, T, max_range, seed, partials,
                    c->d_sums.get(), far_work(c, c->shard_hi - c->shard_lo), c->stream);
     all_reduce_sum(c, c->d_sums.get(), 2);
     GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -67,6 +67,12 @@ class DevBuf {
 // ingest (strided xyz -> float4 + bbox) -> density probe -> cell keys -> radix sort -> reorder -> brick/cell tables.
 class GridIndex {
  public:
+  GridIndex() = default;
+  GridIndex(const GridIndex&) = delete;
+  GridIndex& operator=(const GridIndex&) = delete;
+  ~GridIndex() {
+    if (h_pin_) cudaFreeHost(h_pin_);
+  }
   struct Info {
     int64_t n_points = 0, n_indexed = 0;
     float cell_size = 0;
@@ -104,6 +110,7 @@ class GridIndex {
   DevBuf<int> pos_of_;
   DevBuf<unsigned long long> sb_mask_, hb_mask_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
+  unsigned* h_pin_ = nullptr; // pinned host words the build reads its counters back into
 };
 
 // hand-written device-wide primitives (sort_scan.cu)

@@ -268,8 +268,11 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   GICPB_LAUNCHED();
   ingest_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(d_raw, n, stride_bytes, pts_unsorted_.get(), scratch_.get());
   GICPB_LAUNCHED();
-  unsigned hs[16];
-  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  if (!h_pin_) GICPB_CUDA(cudaHostAlloc(&h_pin_, 32 * sizeof(unsigned), cudaHostAllocDefault));  // read-backs: no staging copy
+  unsigned* hs = h_pin_;                  // 16 words of scratch
+  unsigned* occ = h_pin_ + 16;            // kProbeLevels words of the density probe
+  constexpr size_t kHsBytes = 16 * sizeof(unsigned);
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
   const int64_t n_valid = hs[6];
   info_.n_indexed = n_valid;
@@ -313,8 +316,8 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
       popcount_kernel<<<blocks_for((int64_t)words, 256), 256, 0, stream>>>(occ_bits_.get(), pp, words,
                                                                            occ_bits_.get() + words);
       GICPB_LAUNCHED();
-      unsigned occ[kProbeLevels];
-      GICPB_CUDA(cudaMemcpyAsync(occ, occ_bits_.get() + words, sizeof(occ), cudaMemcpyDeviceToHost, stream));
+      static_assert(kProbeLevels <= 16, "probe read-back buffer");
+      GICPB_CUDA(cudaMemcpyAsync(occ, occ_bits_.get() + words, kProbeLevels * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
       GICPB_CUDA(cudaStreamSynchronize(stream));
       const double N = (double)n_valid / sub;  // sampled points (the non-finite fraction is taken as uniform)
       const double tau = (points_per_cell > 0.f ? points_per_cell : 6.0) / sub;
@@ -410,14 +413,14 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
                                                                     brick_slot_.get(), sb_mask_.get(), hb_mask_.get(),
                                                                     scratch_.get());
   GICPB_LAUNCHED();
-  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
   const int64_t n_slots = hs[7];
   cell_start_.reserve((size_t)n_slots * kBrickCells + 1);
   cell_start_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, cell_start_.get(),
                                                                    scratch_.get());
   GICPB_LAUNCHED();
-  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), sizeof(hs), cudaMemcpyDeviceToHost, stream));
+  GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
 
   g.pts = pts_sorted_.get();

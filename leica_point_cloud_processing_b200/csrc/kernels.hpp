@@ -86,8 +86,9 @@ void launch_correspondences(const GridView& g, const float4* src, int lo, int hi
                             float* pair_d2, float4* pair_tgt, void* maha, bool maha_fp32, bool use_prev,
                             const FarWork& fw, cudaStream_t stream);
 int fitness_partial_rows(int n, int far_blocks);
+// seed: nullptr, or one sorted-target position (-1 = none) per source point of [lo, hi) as a first candidate
 void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
-                    double* partials, double* out2, const FarWork& fw, cudaStream_t stream);
+                    const int* seed, double* partials, double* out2, const FarWork& fw, cudaStream_t stream);
 void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
                        bool always_keep, unsigned char* mask, unsigned long long* kept, const FarWork& fw,
                        cudaStream_t stream);
@@ -133,7 +134,9 @@ struct PeerReduce {
 // makes every entry NaN.
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                  const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream,
-                 const PeerReduce* peer = nullptr);
+                 const PeerReduce* peer = nullptr, unsigned stamp = 0);
+// stamp != 0: out14 must be mapped host memory of 16 doubles; the kernel stores (double)stamp into out14[15] once the 14
+// sums are visible to the host, which can then poll that word instead of synchronising the stream.
 
 // ---- segment.cu -----------------------------------------------------------------------------------------
 // Euclidean clustering: joins every pair of indexed points of `g` with d2 < r2 (strict) in a union-find over sorted

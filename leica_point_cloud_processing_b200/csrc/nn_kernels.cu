@@ -180,10 +180,12 @@ correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi
 }
 
 // fitness: partial (sum d2, count) per block -> partials[(row0 + block)*2 + {0,1}]
+// seed (nullable): pair_pos of the last correspondence pass - the match of each source point under a nearby pose is a
+// first candidate that bounds the search ball (it is only a candidate: the result is the exact nearest neighbour)
 template <bool kFar>
 __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridView g, const float4* __restrict__ src, int lo, int hi,
-                                                              Rigid T, double max_range, double* __restrict__ partials,
-                                                              int row0, FarWork fw) {
+                                                              Rigid T, double max_range, const int* __restrict__ seed,
+                                                              double* __restrict__ partials, int row0, FarWork fw) {
   GICPB_NEAR_QUEUE();
   __shared__ double ssum[4], scnt[4];
   double sum = 0.0, cnt = 0.0;
@@ -191,6 +193,15 @@ __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridV
     const float4 p = __ldg(&src[lo + t]);
     const float3 q = xform(T, p.x, p.y, p.z);
     NNState s = nn_init(0.f);
+    if (seed) {
+      const int prev = __ldg(&seed[t]);
+      if (prev >= 0) {
+        const float4 c = __ldg(&g.pts[prev]);
+        s.best = dist2(q.x, q.y, q.z, c);
+        s.pos = prev;
+        s.oi = __float_as_int(c.w);
+      }
+    }
     bool hit;
     if (finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, t, fw, qb, qe, hit)) return;
     if (s.pos >= 0 && (double)s.best <= max_range) {
@@ -462,7 +473,7 @@ void launch_correspondences(const GridView& g, const float4* src, int lo, int hi
 int fitness_partial_rows(int n, int far_blocks) { return (int)nblocks(n, kNnThreads) + far_blocks; }
 
 void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
-                    double* partials, double* out2, const FarWork& fw, cudaStream_t stream) {
+                    const int* seed, double* partials, double* out2, const FarWork& fw, cudaStream_t stream) {
   const int n = hi - lo;
   if (n <= 0) {
     GICPB_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(double), stream));
@@ -470,9 +481,9 @@ void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const 
   }
   reset_far(fw, n, stream);
   const unsigned nb = nblocks(n, kNnThreads);
-  fitness_kernel<false><<<nb, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, partials, 0, fw);
+  fitness_kernel<false><<<nb, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, seed, partials, 0, fw);
   GICPB_LAUNCHED();
-  fitness_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, partials, (int)nb, fw);
+  fitness_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, seed, partials, (int)nb, fw);
   GICPB_LAUNCHED();
   reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb + fw.far_blocks, 2, out2);
   GICPB_LAUNCHED();
