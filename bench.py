@@ -192,8 +192,7 @@ def run_ours(args):
         # target is being indexed (no-op on device clouds)
         eng.prefetch(0, tgt_buf)
         eng.prefetch(1, src_buf)
-        eng.set_target(tgt_buf)
-        eng.set_source(src_buf)
+        eng.set_clouds(tgt_buf, src_buf)   # index target; its covariances overlap the source's index; source covariances
         res = eng.align()
         fit = eng.fitness(res["transform"])
         return res, fit

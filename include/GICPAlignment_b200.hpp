@@ -342,19 +342,18 @@ class GICPAlignment {
 
   void setInputs() {  // gicp_.setInputSource / setInputTarget, :89-90
     if (source_cloud_->points.empty() || target_cloud_->points.empty()) throw std::runtime_error("empty cloud");
-    // both uploads go to the copy stream, source first: the target uploads while the source is being indexed
-    ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 1, &source_cloud_->points[0].x, (int64_t)source_cloud_->points.size(),
-                                    (int64_t)sizeof(source_cloud_->points[0])),
-               "gicpb_prefetch_cloud");
+    // both uploads go to the copy stream, target first: the source uploads while the target is being indexed; then
+    // one call indexes both clouds and computes their covariances (the target's beside the source's index build)
     ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 0, &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
                                     (int64_t)sizeof(target_cloud_->points[0])),
                "gicpb_prefetch_cloud");
-    ctx_.check(gicpb_set_source(ctx_.get(), &source_cloud_->points[0].x, (int64_t)source_cloud_->points.size(),
-                                (int64_t)sizeof(source_cloud_->points[0]), 0),
-               "gicpb_set_source");
-    ctx_.check(gicpb_set_target(ctx_.get(), &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
-                                (int64_t)sizeof(target_cloud_->points[0]), 0),
-               "gicpb_set_target");
+    ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 1, &source_cloud_->points[0].x, (int64_t)source_cloud_->points.size(),
+                                    (int64_t)sizeof(source_cloud_->points[0])),
+               "gicpb_prefetch_cloud");
+    ctx_.check(gicpb_set_clouds(ctx_.get(), &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
+                                (int64_t)sizeof(target_cloud_->points[0]), &source_cloud_->points[0].x,
+                                (int64_t)source_cloud_->points.size(), (int64_t)sizeof(source_cloud_->points[0]), 0),
+               "gicpb_set_clouds");
     inputs_set_ = true;
   }
 

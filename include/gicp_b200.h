@@ -112,6 +112,12 @@ int gicpb_peer_disable(gicpb_ctx* ctx); /* back to ncclAllReduce (call on every 
 int gicpb_prefetch_cloud(gicpb_ctx* ctx, int which, const void* xyz, int64_t n, int64_t stride_bytes);
 int gicpb_set_target(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
 int gicpb_set_source(gicpb_ctx* ctx, const void* xyz, int64_t n, int64_t stride_bytes, int on_device);
+/* gicpb_set_target + gicpb_set_source + gicpb_compute_covariances in one call, with the same results: the target's
+ * covariance pass runs on a second stream while the source is being indexed (setInputTarget + setInputSource,
+ * src/GICPAlignment.cpp:89-90, and the two computeCovariances passes of gicp_.align, :96).  Both clouds host or both
+ * device; clouds announced with gicpb_prefetch_cloud are taken from there. */
+int gicpb_set_clouds(gicpb_ctx* ctx, const void* target, int64_t n_target, int64_t target_stride_bytes,
+                     const void* source, int64_t n_source, int64_t source_stride_bytes, int on_device);
 /* kNN-k covariances of both clouds, regularised to (1, 1, gicp_epsilon) (PCL GICP::computeCovariances).
  * Called implicitly by gicpb_align when missing; cached until the cloud is set again (PCL A.1 semantics). */
 int gicpb_compute_covariances(gicpb_ctx* ctx);

@@ -117,6 +117,8 @@ _SIGNATURES = [
     ("gicpb_prefetch_cloud", ctypes.c_int, [_VOID_P, ctypes.c_int, _VOID_P, ctypes.c_int64, ctypes.c_int64]),
     ("gicpb_set_target", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     ("gicpb_set_source", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    ("gicpb_set_clouds", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, _VOID_P, ctypes.c_int64,
+                                        ctypes.c_int64, ctypes.c_int]),
     ("gicpb_compute_covariances", ctypes.c_int, [_VOID_P]),
     ("gicpb_align", ctypes.c_int, [_VOID_P, ctypes.POINTER(AlignResult)]),
     ("gicpb_fitness", ctypes.c_int, [_VOID_P, c_float_p, ctypes.c_double, c_double_p]),
@@ -311,6 +313,15 @@ class Engine:
     def set_source(self, cloud):
         keep, ptr, n, stride, dev = self._cloud_args(1, cloud)
         self._check(self.lib.gicpb_set_source(self.h, ptr, n, stride, dev))
+
+    def set_clouds(self, target, source):
+        """set_target + set_source + compute_covariances in one call (the target's covariance pass overlaps the source's
+        index build); both clouds on the host or both on the device."""
+        kt, tptr, tn, tstride, tdev = self._cloud_args(0, target)
+        ks, sptr, sn, sstride, sdev = self._cloud_args(1, source)
+        if tdev != sdev:
+            raise ValueError("set_clouds: both clouds must be host arrays or both device tensors")
+        self._check(self.lib.gicpb_set_clouds(self.h, tptr, tn, tstride, sptr, sn, sstride, tdev))
 
     def compute_covariances(self):
         self._check(self.lib.gicpb_compute_covariances(self.h))

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -168,6 +169,8 @@ struct gicpb_ctx {
   size_t l2_persist_bytes = 0, l2_window_max = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // uploads started by gicpb_prefetch_cloud run here, beside the compute stream
+  cudaStream_t aux_stream = nullptr;   // gicpb_set_clouds: target covariances beside the source index build
+  cudaEvent_t ev_aux = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_order = nullptr;
   struct Prefetch {
     const void* host = nullptr;
@@ -285,24 +288,34 @@ void update_shard(gicpb_ctx* c) {
   c->shard_hi = (int)(n * (c->rank + 1) / c->world);
 }
 
-void ensure_covariances(gicpb_ctx* c) {
-  if (c->cov_ready) return;
-  if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
+// Target covariances are needed in full on every rank, but each is a function of the target cloud alone: every rank
+// computes one contiguous chunk of the (identically sorted) target (start_target_cov, on `knn_stream`) and the chunks
+// are all-gathered in place (finish_covariances, on the context's stream).
+int target_chunk(const gicpb_ctx* c) { return (c->tgt.n_indexed() + c->world - 1) / c->world; }
+
+void check_k(const gicpb_ctx* c) {
   const int k = c->prm.k_correspondences;
   if (k < 2 || k > 32) throw ArgError("k_correspondences must be in [2, 32]");
-  if (k > c->tgt.n_indexed() || k > c->src.n_indexed())
-    throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points in a cloud");
-  update_shard(c);
-  const int ns = c->shard_hi - c->shard_lo;
-  // Target covariances are needed in full on every rank, but each is a function of the target cloud alone: every rank
-  // computes one contiguous chunk of the (identically sorted) target and the chunks are all-gathered in place.
+}
+
+void start_target_cov(gicpb_ctx* c, cudaStream_t knn_stream) {
+  const int k = c->prm.k_correspondences;
   const int nt = c->tgt.n_indexed();
-  const int chunk = (nt + c->world - 1) / c->world;
+  const int chunk = target_chunk(c);
   const int t_lo = std::min(nt, c->rank * chunk), t_hi = std::min(nt, t_lo + chunk);
   c->n_tgt.reserve(3 * (size_t)chunk * c->world);
+  const FarWork fw = far_work(c, chunk);
+  launch_knn_covariances(c->tgt.view(), t_lo, t_hi, k, c->n_tgt.get() + 3 * (size_t)t_lo, nullptr, nullptr, fw, knn_stream);
+}
+
+// the rest, on the context's stream (which must already be ordered after start_target_cov's kernels)
+void finish_covariances(gicpb_ctx* c) {
+  const int k = c->prm.k_correspondences;
+  update_shard(c);
+  const int ns = c->shard_hi - c->shard_lo;
+  const int chunk = target_chunk(c);
   c->n_src.reserve(3 * (size_t)std::max(ns, 1));
   const FarWork fw = far_work(c, std::max(chunk, ns));
-  launch_knn_covariances(c->tgt.view(), t_lo, t_hi, k, c->n_tgt.get() + 3 * (size_t)t_lo, nullptr, nullptr, fw, c->stream);
   if (c->world > 1)
     check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
                                      kNcclFloat64, c->comm, c->stream), "ncclAllGather");
@@ -310,6 +323,17 @@ void ensure_covariances(gicpb_ctx* c) {
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
   c->cov_ready = true;
   c->pairs_valid = false;
+}
+
+void ensure_covariances(gicpb_ctx* c) {
+  if (c->cov_ready) return;
+  if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
+  check_k(c);
+  const int k = c->prm.k_correspondences;
+  if (k > c->tgt.n_indexed() || k > c->src.n_indexed())
+    throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points in a cloud");
+  start_target_cov(c, c->stream);
+  finish_covariances(c);
 }
 
 void ensure_pair_buffers(gicpb_ctx* c) {
@@ -646,8 +670,21 @@ int gicpb_create(int device, gicpb_ctx** out) {
       c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     }
     cudaGetLastError();
-    GICPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     GICPB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    {
+      // gicpb_set_clouds runs the target's covariance pass on aux_stream beside the source's index build on the main
+      // stream.  The build is a chain of short kernels and read-backs: its blocks must get onto the SMs as soon as
+      // they are launched, so the main stream has the highest priority and aux_stream the lowest, and the build's
+      // kernels ask for the same (largest) shared-memory carve-out as the kNN kernel so that both can share an SM
+      // (measured at 1 M + 1 M points: 2.34 ms for the separate calls, 2.21 ms overlapped, 2.07 ms with both hints).
+      int lo_p = 0, hi_p = 0;
+      GICPB_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+      GICPB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi_p));
+      GICPB_CUDA(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, lo_p));
+      prefer_shared_carveout_grid();
+      prefer_shared_carveout_sort();
+    }
+    GICPB_CUDA(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
     GICPB_CUDA(cudaEventCreate(&c->ev0));
     GICPB_CUDA(cudaEventCreate(&c->ev1));
     GICPB_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
@@ -684,6 +721,8 @@ void gicpb_destroy(gicpb_ctx* c) {
   }
   if (c->ev_order) cudaEventDestroy(c->ev_order);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->ev_aux) cudaEventDestroy(c->ev_aux);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -838,6 +877,51 @@ int gicpb_set_source(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, i
     }
     c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
     update_shard(c);
+  });
+}
+
+// Both clouds in one call: the target is indexed, then its kNN covariances run on a second stream WHILE the source is
+// indexed on the context's stream (the index build is a chain of small kernels and read-backs that leaves most of
+// the GPU idle; the kNN kernel fills it), then the source covariances.  Same results as set_target + set_source +
+// compute_covariances.  When k_correspondences does not fit the clouds the covariances are left to gicpb_align, which
+// reports it as before.
+int gicpb_set_clouds(gicpb_ctx* c, const void* target, int64_t n_target, int64_t target_stride, const void* source,
+                     int64_t n_source, int64_t source_stride, int on_device) {
+  return guarded(c, [&] {
+    check_cloud_args(target, n_target, target_stride);
+    check_cloud_args(source, n_source, source_stride);
+    c->cov_ready = false;
+    c->pairs_valid = false;
+    int t_dev = on_device, s_dev = on_device;
+    if (take_prefetch(c, 0, target, n_target, target_stride, on_device)) {
+      target = c->prefetch[0].dev;
+      t_dev = 1;
+    }
+    c->tgt.build(target, n_target, target_stride, t_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    const int k = c->prm.k_correspondences;
+    const bool overlap = k >= 2 && k <= 32 && k <= c->tgt.n_indexed();
+    if (overlap) {  // the build has synchronised c->stream: the index is complete
+      start_target_cov(c, c->aux_stream);
+      GICPB_CUDA(cudaEventRecord(c->ev_aux, c->aux_stream));
+    }
+    try {
+      if (take_prefetch(c, 1, source, n_source, source_stride, on_device)) {
+        source = c->prefetch[1].dev;
+        s_dev = 1;
+      }
+      c->src.build(source, n_source, source_stride, s_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    } catch (...) {
+      if (overlap) cudaStreamSynchronize(c->aux_stream);  // nothing may still be running on the target when we leave
+      throw;
+    }
+    if (overlap) {
+      GICPB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
+      if (k <= c->src.n_indexed()) {
+        finish_covariances(c);
+      } else {
+        GICPB_CUDA(cudaStreamSynchronize(c->stream));
+      }
+    }
   });
 }
 

@@ -113,6 +113,11 @@ class GridIndex {
   unsigned* h_pin_ = nullptr; // pinned host words the build reads its counters back into
 };
 
+// the index-build kernels ask for the largest shared-memory carve-out, like the kNN kernel they may share an SM with
+// (gicpb_set_clouds); called once per context
+void prefer_shared_carveout_grid();
+void prefer_shared_carveout_sort();
+
 // hand-written device-wide primitives (sort_scan.cu)
 // Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  Returns true if the result is in
 // the *_b buffers, false if in *_a.  hist must hold 256 * ceil(n / 2048) + 1024 entries.

@@ -243,6 +243,22 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 
 }  // namespace
 
+// Ask for the largest shared-memory carve-out on every index-build kernel so that their blocks can share an SM with the
+// kNN kernel (which needs it) when both run on different streams (gicpb_set_clouds).
+void prefer_shared_carveout_grid() {
+  const int pct = 100;
+  cudaFuncSetAttribute(init_scratch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(ingest_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(popcount_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(keys_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(brick_flags_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(brick_slots_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(cell_start_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  (void)cudaGetLastError();
+}
+
 void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
                       float points_per_cell, cudaStream_t stream) {
   const auto t_begin = std::chrono::steady_clock::now();

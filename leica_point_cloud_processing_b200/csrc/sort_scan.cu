@@ -170,6 +170,16 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
 
 }  // namespace
 
+void prefer_shared_carveout_sort() {  // see prefer_shared_carveout_grid (grid_build.cu)
+  const int pct = 100;
+  cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(scan_reduce_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(scan_spine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(scan_down_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  (void)cudaGetLastError();
+}
+
 size_t scan_tmp_entries(int64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile) + 1; }
 size_t radix_sort_hist_entries(int64_t n) { return 256 * (size_t)((n + kSortTile - 1) / kSortTile) + 1024; }
 

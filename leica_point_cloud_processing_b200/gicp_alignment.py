@@ -158,10 +158,9 @@ class GICPAlignment:
     def _fine_alignment(self):
         # reference :86-109
         log.info("Perform GICP with %d iterations", self.max_iter_)
-        self._engine.prefetch(1, self.source_cloud_)   # both uploads queue on the copy stream, source first:
-        self._engine.prefetch(0, self.target_cloud_)   # the target uploads while the source is indexed
-        self._engine.set_source(self.source_cloud_)
-        self._engine.set_target(self.target_cloud_)
+        self._engine.prefetch(0, self.target_cloud_)   # both uploads queue on the copy stream, target first:
+        self._engine.prefetch(1, self.source_cloud_)   # the source uploads while the target is indexed
+        self._engine.set_clouds(self.target_cloud_, self.source_cloud_)
         self._inputs_set = True
         res = self._engine.align(raise_on_failure=False)
         self.last_result = res
@@ -183,8 +182,7 @@ class GICPAlignment:
         self.backup_cloud_ = _copy(self.aligned_cloud_) if self.aligned_cloud_ is not None else None
         log.info("Computing iteration...")
         if not self._inputs_set:
-            self._engine.set_source(self.source_cloud_)
-            self._engine.set_target(self.target_cloud_)
+            self._engine.set_clouds(self.target_cloud_, self.source_cloud_)
             self._inputs_set = True
         res = self._engine.align(raise_on_failure=False)
         self.last_result = res

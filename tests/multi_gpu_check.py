@@ -42,8 +42,11 @@ def main():
         for name, s, t, prm in cases:
             name = f"[{mode}] {name}"
             eng.set_params(**{**dict(max_corr_distance=4e-2, transformation_epsilon=4e-3), **prm})
-            eng.set_target(t)
-            eng.set_source(s)
+            if mode == "peer":
+                eng.set_clouds(t, s)   # target covariance chunk on the second stream beside the source index, then all-gather
+            else:
+                eng.set_target(t)
+                eng.set_source(s)
             res = eng.align()
             fit = eng.fitness(res["transform"])
             ref = orc.align(s, t, default_params(**prm))

@@ -23,7 +23,7 @@ def build(tmp_path, std="c++14"):
 def test_shim_compiles_and_links(tmp_path):
     exe = build(tmp_path)
     out = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
-    for sym in ("gicpb_create", "gicpb_align", "gicpb_set_source", "gicpb_set_target", "gicpb_fitness",
+    for sym in ("gicpb_create", "gicpb_align", "gicpb_set_clouds", "gicpb_fitness",
                 "gicpb_transform_cloud", "gicpb_cloud_difference", "gicpb_euclidean_clusters", "gicpb_voxel_grid",
                 "gicpb_pointcloud2_to_xyzrgb", "gicpb_pcd_load_xyzrgb"):
         assert sym in out

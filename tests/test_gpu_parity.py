@@ -291,6 +291,48 @@ def test_prefetched_uploads_give_the_same_result(engine, oracle, cube_pair):
     assert np.array_equal(idx, oi) and np.array_equal(d2, od)
 
 
+def test_set_clouds_equals_the_separate_calls(engine, oracle, cube_pair):
+    """gicpb_set_clouds = set_target + set_source + compute_covariances with the target's covariance pass on a second
+    stream beside the source's index build: covariances bit-identical, same transform and fitness; host, prefetched host
+    and device clouds; a cloud smaller than k leaves the error to align, as before."""
+    import torch
+    from leica_point_cloud_processing_b200 import synth
+    src, tgt, _ = cube_pair
+    big_s, big_t, _ = synth.make_pair(60_000, 80_000)
+    for s_, t_, gate in ((src, tgt, 5.0), (big_s, big_t, 1.0)):
+        reset(engine, max_corr_distance=gate, transformation_epsilon=5e-4)
+        engine.set_target(t_)
+        engine.set_source(s_)
+        engine.compute_covariances()
+        c0t, c0s = engine.covariances(0), engine.covariances(1)
+        plain = engine.align()
+        f0 = engine.fitness(plain["transform"])
+        for mode in ("host", "prefetched", "device"):
+            if mode == "prefetched":
+                engine.prefetch(0, t_)
+                engine.prefetch(1, s_)
+            a, b = (torch.from_numpy(t_).cuda(), torch.from_numpy(s_).cuda()) if mode == "device" else (t_, s_)
+            engine.set_clouds(a, b)
+            assert np.array_equal(engine.covariances(0), c0t) and np.array_equal(engine.covariances(1), c0s), mode
+            both = engine.align()
+            assert np.array_equal(plain["transform"], both["transform"]), mode
+            assert both["outer_iterations"] == plain["outer_iterations"]
+            assert engine.fitness(both["transform"]) == f0
+    idx, d2 = engine.nn1(big_s)
+    oi, od = oracle.nn1(big_t, big_s)
+    assert np.array_equal(idx, oi) and np.array_equal(d2, od)
+    # fewer points than k_correspondences in either cloud: set_clouds succeeds, align reports -7 (PCL: error + return)
+    reset(engine, max_corr_distance=5.0)
+    engine.set_clouds(tgt[:10], src)
+    assert engine.align(raise_on_failure=False)["rc"] == -7
+    engine.set_clouds(tgt, src[:10])
+    assert engine.align(raise_on_failure=False)["rc"] == -7
+    engine.set_clouds(tgt, src)
+    assert engine.align()["converged"] == 1
+    with pytest.raises(Exception):
+        engine.set_clouds(tgt, src[:0])
+
+
 def test_align_not_enough_correspondences(engine, cube_pair):
     src, tgt, _ = cube_pair
     reset(engine, max_corr_distance=1e-4)
