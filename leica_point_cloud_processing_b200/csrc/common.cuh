@@ -50,7 +50,14 @@ GICPB_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
 GICPB_HD float fsub(float a, float b) { return __fsub_rn(a, b); }
 GICPB_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
 GICPB_HD int floor_to_int(float v) { return __float2int_rd(v); }
-GICPB_HD float sqrt_up(float v) { return __fsqrt_ru(v); }
+// an upper bound of sqrt(v), only ever used to size a search box: the approximate square root (MUFU.SQRT, relative
+// error <= 2^-23) times 1 + 2^-21 is never below the true root and costs two instructions instead of the
+// range-checked Newton sequence of __fsqrt_ru
+GICPB_HD float sqrt_up(float v) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return __fmul_ru(r, 1.00000047683715820312f);
+}
 GICPB_HD int ffs64(unsigned long long m) { return __ffsll((long long)m); }
 template <typename T>
 GICPB_HD T ldg(const T* p) { return __ldg(p); }

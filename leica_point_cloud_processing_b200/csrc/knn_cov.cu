@@ -162,10 +162,12 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   const size_t heap = (size_t)2 * k * kKnnFarThreads * sizeof(int);
   const size_t queue = (size_t)2 * kKnnQueueCap * kKnnNearThreads * sizeof(unsigned);
   const unsigned nb = (unsigned)((n + kKnnNearThreads - 1) / kKnnNearThreads);
-  static bool attr_set = false;
-  if (!attr_set) {  // 64 KB of dynamic shared memory at k = 32
+  static unsigned long long attr_set = 0ull;  // one bit per device: the attribute belongs to the device's context
+  int dev = 0;
+  GICPB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {  // up to 88 KB of dynamic shared memory at k = 32
     GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+    if (dev < 64) attr_set |= 1ull << dev;
   }
   knn_cov_kernel<false><<<nb, kKnnNearThreads, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
   GICPB_LAUNCHED();
