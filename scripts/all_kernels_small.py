@@ -1,5 +1,7 @@
-"""A small pass through every kernel of the library, meant to be run under compute-sanitizer:
-   compute-sanitizer --tool memcheck python scripts/sanitize_small.py"""
+"""A small pass through every kernel of the library with cross-checks between equivalent call paths (set_clouds against
+the separate calls, aligned against byte-wise PointCloud2 gathers).  Written for compute-sanitizer
+(`compute-sanitizer --tool memcheck python scripts/all_kernels_small.py`); that tool is closed on this GPU pool, so it
+serves as a quick functional pass instead."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
