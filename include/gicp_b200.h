@@ -13,6 +13,8 @@
  *     (x, y, z are three consecutive float32).  stride 32 = pcl::PointXYZRGB as the reference holds it
  *     (include/GICPAlignment.h:35), stride 16 = float4, stride 12 = packed xyz
  *   - `on_device` != 0 means the pointer is a CUDA device pointer on the context's GPU; otherwise host
+ *     (pinned host memory is copied as it is; pageable host clouds of 8 MB and more - a pcl::PointCloud - are gathered
+ *     into packed xyz rows by a few host threads through a ring of pinned chunks, so 12 bytes per point cross PCIe)
  *   - 4x4 transforms are float32, ROW-major (T[4*r + c]); Eigen::Matrix4f is column-major, the shim transposes
  *   - a context is bound to one GPU and is not thread-safe; distinct contexts are independent
  *   - there is no CPU fallback: without a usable GPU gicpb_create fails with GICPB_E_CUDA

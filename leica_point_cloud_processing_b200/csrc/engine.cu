@@ -176,6 +176,7 @@ struct gicpb_ctx {
     const void* host = nullptr;
     int64_t n = 0, stride = 0;
     unsigned char* dev = nullptr;
+    int64_t dev_stride = 0;  // stride of the device copy (12 when the cloud went through the packed staged upload)
     cudaEvent_t done = nullptr;
     bool pending = false;
   } prefetch[2];  // 0 target, 1 source
@@ -208,6 +209,7 @@ struct gicpb_ctx {
   unsigned* h_far = nullptr;      // pinned: far-query count of the last correspondence pass
   DevBuf<float4> queries;
   DevBuf<unsigned char> io_a, io_b;
+  HostStager stager;              // pageable host clouds reach the device through its pinned ring (upload.hpp)
   DevBuf<unsigned long long> counter;
   DevBuf<unsigned char> far_flags;  // near -> far hand-over (kernels.hpp FarWork)
   DevBuf<unsigned> far_counter;
@@ -591,12 +593,17 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
   if (status == GICPB_E_SOLVER) c->err = "BFGS did not converge";
 }
 
-const unsigned char* stage_in(gicpb_ctx* c, DevBuf<unsigned char>& buf, const void* p, int64_t n, int64_t stride,
+// xyz of a host cloud onto the device (only x, y, z are read from the staged copy); *stride becomes the stride of the copy
+const unsigned char* stage_in(gicpb_ctx* c, DevBuf<unsigned char>& buf, const void* p, int64_t n, int64_t* stride,
                               bool on_device) {
   if (on_device) return static_cast<const unsigned char*>(p);
-  const size_t bytes = (size_t)(n - 1) * stride + 12;
-  buf.reserve((size_t)n * stride);
-  GICPB_CUDA(cudaMemcpyAsync(buf.get(), p, bytes, cudaMemcpyHostToDevice, c->stream));
+  buf.reserve((size_t)n * *stride);
+  if (HostStager::wants(p, n, *stride)) {
+    c->stager.upload(buf.get(), static_cast<const unsigned char*>(p), n, *stride, 12, c->stream);
+    *stride = 12;
+  } else {
+    GICPB_CUDA(cudaMemcpyAsync(buf.get(), p, (size_t)(n - 1) * *stride + 12, cudaMemcpyHostToDevice, c->stream));
+  }
   return buf.get();
 }
 
@@ -844,7 +851,13 @@ int gicpb_prefetch_cloud(gicpb_ctx* c, int which, const void* xyz, int64_t n, in
     GICPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
     GridIndex& g = which == 0 ? c->tgt : c->src;
     p.dev = g.stage((size_t)n * stride);
-    GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
+    p.dev_stride = stride;
+    if (HostStager::wants(xyz, n, stride)) {  // pageable: packed xyz rows (this call then lasts as long as the gather)
+      c->stager.upload(p.dev, static_cast<const unsigned char*>(xyz), n, stride, 12, c->copy_stream);
+      p.dev_stride = 12;
+    } else {
+      GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
+    }
     GICPB_CUDA(cudaEventRecord(p.done, c->copy_stream));
     p.host = xyz;
     p.n = n;
@@ -860,9 +873,10 @@ int gicpb_set_target(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, i
     c->pairs_valid = false;
     if (take_prefetch(c, 0, xyz, n, stride, on_device)) {
       xyz = c->prefetch[0].dev;
+      stride = c->prefetch[0].dev_stride;
       on_device = 1;
     }
-    c->tgt.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    c->tgt.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
   });
 }
 
@@ -873,9 +887,10 @@ int gicpb_set_source(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, i
     c->pairs_valid = false;
     if (take_prefetch(c, 1, xyz, n, stride, on_device)) {
       xyz = c->prefetch[1].dev;
+      stride = c->prefetch[1].dev_stride;
       on_device = 1;
     }
-    c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
     update_shard(c);
   });
 }
@@ -895,9 +910,10 @@ int gicpb_set_clouds(gicpb_ctx* c, const void* target, int64_t n_target, int64_t
     int t_dev = on_device, s_dev = on_device;
     if (take_prefetch(c, 0, target, n_target, target_stride, on_device)) {
       target = c->prefetch[0].dev;
+      target_stride = c->prefetch[0].dev_stride;
       t_dev = 1;
     }
-    c->tgt.build(target, n_target, target_stride, t_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    c->tgt.build(target, n_target, target_stride, t_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
     const int k = c->prm.k_correspondences;
     const bool overlap = k >= 2 && k <= 32 && k <= c->tgt.n_indexed();
     if (overlap) {  // the build has synchronised c->stream: the index is complete
@@ -907,9 +923,10 @@ int gicpb_set_clouds(gicpb_ctx* c, const void* target, int64_t n_target, int64_t
     try {
       if (take_prefetch(c, 1, source, n_source, source_stride, on_device)) {
         source = c->prefetch[1].dev;
+        source_stride = c->prefetch[1].dev_stride;
         s_dev = 1;
       }
-      c->src.build(source, n_source, source_stride, s_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+      c->src.build(source, n_source, source_stride, s_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
     } catch (...) {
       if (overlap) cudaStreamSynchronize(c->aux_stream);  // nothing may still be running on the target when we leave
       throw;
@@ -980,7 +997,7 @@ int gicpb_transform_cloud(gicpb_ctx* c, const float transform[16], const void* i
 int gicpb_difference_set_subtract(gicpb_ctx* c, const void* subtract, int64_t n, int64_t stride, int on_device) {
   return guarded(c, [&] {
     check_cloud_args(subtract, n, stride);
-    c->sub.build(subtract, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream);
+    c->sub.build(subtract, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
   });
 }
 
@@ -991,7 +1008,7 @@ int gicpb_difference_run(gicpb_ctx* c, const void* input, int64_t n, int64_t str
     check_cloud_args(input, n, stride);
     if (!c->sub.ready()) throw StateError("difference_set_subtract must be called first");
     if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
-    const unsigned char* d_in = stage_in(c, c->io_a, input, n, stride, on_device != 0);
+    const unsigned char* d_in = stage_in(c, c->io_a, input, n, &stride, on_device != 0);
     unsigned char* d_mask = mask;
     if (!mask_on_device) {
       c->io_b.reserve((size_t)n);
@@ -1033,7 +1050,7 @@ int gicpb_nn1(gicpb_ctx* c, const void* queries, int64_t n, int64_t stride, int 
     float ident[16];
     identity16(ident);
     const Rigid T = rigid_from_rowmajor(transform ? transform : ident);
-    const unsigned char* d_in = stage_in(c, c->io_a, queries, n, stride, on_device != 0);
+    const unsigned char* d_in = stage_in(c, c->io_a, queries, n, &stride, on_device != 0);
     c->queries.reserve((size_t)n);
     launch_pack_queries(d_in, n, stride, c->queries.get(), c->stream);
     c->io_b.reserve((size_t)n * 8);
@@ -1226,7 +1243,7 @@ int gicpb_euclidean_clusters(gicpb_ctx* c, const void* cloud, int64_t n, int64_t
     // cells of the tolerance: the ball of a query cuts at most 3 x 3 x 3 of them
     bool any_finite = true;
     try {
-      c->clu.build(cloud, n, stride, on_device != 0, (float)tolerance, c->prm.points_per_cell, c->stream);
+      c->clu.build(cloud, n, stride, on_device != 0, (float)tolerance, c->prm.points_per_cell, c->stream, &c->stager);
     } catch (const ArgError& e) {
       if (std::string(e.what()) != "cloud has no finite point") throw;
       any_finite = false;

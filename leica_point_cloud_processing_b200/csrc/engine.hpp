@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "upload.hpp"
 
 namespace gicpb {
 
@@ -82,8 +83,9 @@ class GridIndex {
     float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
   };
   // `raw` points at the first x; device pointer iff on_device.  cell_size <= 0 -> from density.
+  // stager (nullable): pageable host clouds are uploaded through it as packed xyz rows (upload.hpp)
   void build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
-             float points_per_cell, cudaStream_t stream);
+             float points_per_cell, cudaStream_t stream, HostStager* stager = nullptr);
   bool ready() const { return ready_; }
   const GridView& view() const { return view_; }
   const Info& info() const { return info_; }

@@ -260,7 +260,7 @@ void prefer_shared_carveout_grid() {
 }
 
 void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
-                      float points_per_cell, cudaStream_t stream) {
+                      float points_per_cell, cudaStream_t stream, HostStager* stager) {
   const auto t_begin = std::chrono::steady_clock::now();
   ready_ = false;
   if (n <= 0) throw ArgError("cloud is empty");
@@ -274,7 +274,12 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   const unsigned char* d_raw = static_cast<const unsigned char*>(raw);
   if (!on_device) {
     raw_.reserve((size_t)n * stride_bytes);
-    GICPB_CUDA(cudaMemcpyAsync(raw_.get(), raw, (size_t)(n - 1) * stride_bytes + 12, cudaMemcpyHostToDevice, stream));
+    if (stager && HostStager::wants(raw, n, stride_bytes)) {  // pageable memory: packed xyz rows through pinned chunks
+      stager->upload(raw_.get(), static_cast<const unsigned char*>(raw), n, stride_bytes, 12, stream);
+      stride_bytes = 12;
+    } else {
+      GICPB_CUDA(cudaMemcpyAsync(raw_.get(), raw, (size_t)(n - 1) * stride_bytes + 12, cudaMemcpyHostToDevice, stream));
+    }
     d_raw = raw_.get();
   }
   pts_unsorted_.reserve(n);

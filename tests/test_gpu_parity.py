@@ -333,6 +333,42 @@ def test_set_clouds_equals_the_separate_calls(engine, oracle, cube_pair):
         engine.set_clouds(tgt, src[:0])
 
 
+def test_pageable_host_clouds_take_the_staged_upload(engine, oracle):
+    """Large pageable host clouds (pcl::PointCloud memory: 32-byte rows) are gathered into packed xyz rows through a ring
+    of pinned chunks (csrc/upload.hpp) instead of one pageable cudaMemcpy: same index, same answers as device clouds,
+    for set_clouds (with and without prefetch), set_target / set_source, the difference input and NN-1 queries."""
+    import torch
+    from leica_point_cloud_processing_b200 import synth
+    n = 700_000                                   # 22 MB per cloud at 32 bytes per point: three 8 MB chunks
+    src3, tgt3, _ = synth.make_pair(n, n)
+    def rows32(xyz):
+        r = np.full((len(xyz), 8), 7.5, np.float32)  # the other 20 bytes must not matter
+        r[:, :3] = xyz
+        return r
+    src, tgt = rows32(src3), rows32(tgt3)
+    reset(engine, max_corr_distance=1.0, points_per_cell=6.0)
+    engine.set_clouds(torch.from_numpy(tgt3).cuda(), torch.from_numpy(src3).cuda())
+    ref = engine.align()
+    qi, qd = engine.nn1(torch.from_numpy(src3).cuda())
+    for mode in ("set_clouds", "prefetched", "separate"):
+        if mode == "prefetched":
+            engine.prefetch(0, tgt)
+            engine.prefetch(1, src)
+        if mode == "separate":
+            engine.set_target(tgt)
+            engine.set_source(src)
+        else:
+            engine.set_clouds(tgt, src)
+        res = engine.align()
+        assert np.array_equal(res["transform"], ref["transform"]), mode
+        assert res["cost_evaluations"] == ref["cost_evaluations"]
+    i2, d2 = engine.nn1(src)                      # staged query upload, stride 32 -> 12
+    assert np.array_equal(i2, qi) and np.array_equal(d2, qd)
+    m_dev, k_dev = engine.cloud_difference(torch.from_numpy(src3).cuda(), torch.from_numpy(tgt3).cuda(), 4e-4)
+    m_host, k_host = engine.cloud_difference(src, tgt, 4e-4)
+    assert k_host == k_dev and np.array_equal(m_host, m_dev.cpu().numpy())
+
+
 def test_align_not_enough_correspondences(engine, cube_pair):
     src, tgt, _ = cube_pair
     reset(engine, max_corr_distance=1e-4)
