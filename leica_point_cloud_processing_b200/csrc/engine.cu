@@ -593,6 +593,14 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
   if (status == GICPB_E_SOLVER) c->err = "BFGS did not converge";
 }
 
+// `bytes` of host memory onto the device as they are: through the pinned ring when the memory is pageable and large
+void upload_bytes(gicpb_ctx* c, unsigned char* dst, const void* src, size_t bytes) {
+  if (HostStager::wants(src, (int64_t)bytes, 1))
+    c->stager.upload(dst, static_cast<const unsigned char*>(src), (int64_t)bytes, 1, 1, c->stream);
+  else
+    GICPB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+}
+
 // xyz of a host cloud onto the device (only x, y, z are read from the staged copy); *stride becomes the stride of the copy
 const unsigned char* stage_in(gicpb_ctx* c, DevBuf<unsigned char>& buf, const void* p, int64_t n, int64_t* stride,
                               bool on_device) {
@@ -987,7 +995,7 @@ int gicpb_transform_cloud(gicpb_ctx* c, const float transform[16], const void* i
     const size_t bytes = (size_t)(n - 1) * stride + 12;
     const size_t full = (size_t)n * stride;
     c->io_a.reserve(full);
-    GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), in, bytes, cudaMemcpyHostToDevice, c->stream));
+    upload_bytes(c, c->io_a.get(), in, bytes);
     launch_transform(c->io_a.get(), c->io_a.get(), n, stride, T, c->stream);
     GICPB_CUDA(cudaMemcpyAsync(out, c->io_a.get(), bytes, cudaMemcpyDeviceToHost, c->stream));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1302,7 +1310,7 @@ int gicpb_voxel_grid(gicpb_ctx* c, const void* in, int64_t n, int64_t stride, in
       c->io_a.reserve(full);
       c->io_b.reserve(full);
       GICPB_CUDA(cudaMemsetAsync(c->io_a.get() + bytes, 0, full - bytes, c->stream));
-      GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), in, bytes, cudaMemcpyHostToDevice, c->stream));
+      upload_bytes(c, c->io_a.get(), in, bytes);
       d_in = c->io_a.get();
       d_out = c->io_b.get();
     }
@@ -1345,7 +1353,7 @@ void unpack_pc2(gicpb_ctx* c, const void* data, bool data_on_device, const gicpb
   const unsigned char* d_in = static_cast<const unsigned char*>(data);
   if (!data_on_device) {
     c->io_a.reserve(in_bytes);
-    GICPB_CUDA(cudaMemcpyAsync(c->io_a.get(), data, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    upload_bytes(c, c->io_a.get(), data, in_bytes);
     d_in = c->io_a.get();
   }
   float4* d_out = static_cast<float4*>(points32);

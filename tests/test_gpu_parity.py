@@ -367,6 +367,12 @@ def test_pageable_host_clouds_take_the_staged_upload(engine, oracle):
     m_dev, k_dev = engine.cloud_difference(torch.from_numpy(src3).cuda(), torch.from_numpy(tgt3).cuda(), 4e-4)
     m_host, k_host = engine.cloud_difference(src, tgt, 4e-4)
     assert k_host == k_dev and np.array_equal(m_host, m_dev.cpu().numpy())
+    # whole rows through the same ring: transform (all 32 bytes travel) and the PointCloud2 gather
+    moved = engine.transform_cloud(ref["transform"], src)
+    moved_dev = engine.transform_cloud(ref["transform"], torch.from_numpy(src).cuda())
+    assert np.array_equal(moved, moved_dev.cpu().numpy()) and np.all(moved[:, 4:] == 7.5)
+    rows = engine.pointcloud2_to_xyzrgb(src, n, 1, 32, 32 * n, 0, 4, 8, 16)
+    assert np.array_equal(rows[:, :3], src3) and np.all(rows[:, 3] == 1) and np.all(rows[:, 4] == 7.5)
 
 
 def test_align_not_enough_correspondences(engine, cube_pair):
