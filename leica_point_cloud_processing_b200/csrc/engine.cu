@@ -601,6 +601,16 @@ void upload_bytes(gicpb_ctx* c, unsigned char* dst, const void* src, size_t byte
     GICPB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
 }
 
+// `bytes` of device memory into host memory; the stream is synchronised when this returns
+void download_bytes(gicpb_ctx* c, void* dst, const unsigned char* src_dev, size_t bytes) {
+  if (HostStager::wants(dst, (int64_t)bytes, 1)) {
+    c->stager.download(static_cast<unsigned char*>(dst), src_dev, bytes, c->stream);
+  } else {
+    GICPB_CUDA(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  }
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 // xyz of a host cloud onto the device (only x, y, z are read from the staged copy); *stride becomes the stride of the copy
 const unsigned char* stage_in(gicpb_ctx* c, DevBuf<unsigned char>& buf, const void* p, int64_t n, int64_t* stride,
                               bool on_device) {
@@ -997,8 +1007,7 @@ int gicpb_transform_cloud(gicpb_ctx* c, const float transform[16], const void* i
     c->io_a.reserve(full);
     upload_bytes(c, c->io_a.get(), in, bytes);
     launch_transform(c->io_a.get(), c->io_a.get(), n, stride, T, c->stream);
-    GICPB_CUDA(cudaMemcpyAsync(out, c->io_a.get(), bytes, cudaMemcpyDeviceToHost, c->stream));
-    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    download_bytes(c, out, c->io_a.get(), bytes);
   });
 }
 
@@ -1035,7 +1044,7 @@ int gicpb_difference_run(gicpb_ctx* c, const void* input, int64_t n, int64_t str
                       c->stream);
     unsigned long long kept = 0;
     GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
-    if (!mask_on_device) GICPB_CUDA(cudaMemcpyAsync(mask, d_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (!mask_on_device) download_bytes(c, mask, d_mask, (size_t)n);
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
     if (n_kept) *n_kept = (int64_t)kept;
   });
@@ -1328,8 +1337,7 @@ int gicpb_voxel_grid(gicpb_ctx* c, const void* in, int64_t n, int64_t stride, in
       return;
     }
     if (!on_device && m > 0)
-      GICPB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)(m - 1) * stride + std::min<size_t>((size_t)stride, 20), cudaMemcpyDeviceToHost,
-                                 c->stream));
+      download_bytes(c, out, d_out, (size_t)(m - 1) * stride + std::min<size_t>((size_t)stride, 20));
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
     *n_out = m;
   });
@@ -1364,7 +1372,7 @@ void unpack_pc2(gicpb_ctx* c, const void* data, bool data_on_device, const gicpb
     throw ArgError("device output must be 16-byte aligned");
   }
   launch_pc2_unpack(d_in, n, L.width, L.point_step, L.row_step, L.off_x, L.off_y, L.off_z, L.off_rgb, d_out, c->stream);
-  if (!points_on_device) GICPB_CUDA(cudaMemcpyAsync(points32, d_out, (size_t)n * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (!points_on_device) download_bytes(c, points32, reinterpret_cast<const unsigned char*>(d_out), (size_t)n * 32);
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
 }
 }  // namespace

@@ -60,4 +60,33 @@ void HostStager::upload(unsigned char* dst, const unsigned char* src, int64_t n,
   }
 }
 
+void HostStager::download(unsigned char* dst, const unsigned char* src_dev, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return;
+  for (int s = 0; s < kSlots; ++s) {
+    if (!slot_[s]) GICPB_CUDA(cudaHostAlloc(&slot_[s], kChunkBytes, cudaHostAllocDefault));
+    if (!done_[s]) GICPB_CUDA(cudaEventCreateWithFlags(&done_[s], cudaEventDisableTiming));
+    if (used_[s]) GICPB_CUDA(cudaEventSynchronize(done_[s]));  // an earlier upload may still read the slot
+    used_[s] = false;
+  }
+  const int threads = std::max(1, std::min(4, omp_get_max_threads()));
+  const size_t n_chunks = (bytes + kChunkBytes - 1) / kChunkBytes;
+  auto issue = [&](size_t i) {
+    const size_t off = i * kChunkBytes, len = std::min(kChunkBytes, bytes - off);
+    GICPB_CUDA(cudaMemcpyAsync(slot_[i % kSlots], src_dev + off, len, cudaMemcpyDeviceToHost, stream));
+    GICPB_CUDA(cudaEventRecord(done_[i % kSlots], stream));
+  };
+  for (size_t i = 0; i < std::min<size_t>(n_chunks, kSlots - 1); ++i) issue(i);  // two chunks in flight
+  for (size_t i = 0; i < n_chunks; ++i) {
+    if (i + kSlots - 1 < n_chunks) issue(i + kSlots - 1);  // its slot was copied out in the last iteration
+    GICPB_CUDA(cudaEventSynchronize(done_[i % kSlots]));
+    const size_t off = i * kChunkBytes, len = std::min(kChunkBytes, bytes - off);
+    const unsigned char* in = slot_[i % kSlots];
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int t = 0; t < threads; ++t) {
+      const size_t a = len * t / threads, b = len * (t + 1) / threads;
+      std::memcpy(dst + off + a, in + a, b - a);
+    }
+  }
+}
+
 }  // namespace gicpb

@@ -23,6 +23,9 @@ class HostStager {
   // dst[r * row_bytes ..] = src[r * stride ..][0 .. row_bytes) for r < n, queued on `stream`.  Returns once the last
   // chunk has been handed to the copy engine: the caller's memory is not read after that.
   void upload(unsigned char* dst, const unsigned char* src, int64_t n, int64_t stride, int row_bytes, cudaStream_t stream);
+  // the other way: `bytes` of device memory into pageable host memory `dst` (chunks land in the pinned ring and are
+  // copied out by the host threads while the next chunk is in flight).  Synchronous: `dst` is complete on return.
+  void download(unsigned char* dst, const unsigned char* src_dev, size_t bytes, cudaStream_t stream);
 
  private:
   static constexpr size_t kChunkBytes = 8u << 20;

@@ -20,3 +20,11 @@ t("pinned host   ", lambda: eng.cloud_difference(pf, pt, 4e-4))
 df, dt_ = pf.cuda(), pt.cuda()
 t("device        ", lambda: eng.cloud_difference(df, dt_, 4e-4))
 t0 = time.perf_counter(); eng.difference_set_subtract(dt_) if hasattr(eng, "difference_set_subtract") else None; print("set_subtract", (time.perf_counter() - t0) * 1e3)
+# whole rows both ways: pcl::transformPointCloud of 10 M PointXYZRGB rows held in pageable / pinned host memory / on the device
+rows = np.zeros((n, 8), np.float32); rows[:, :3] = src; rows[:, 3] = 1
+Tm = np.eye(4, dtype=np.float32); Tm[0, 3] = 0.5
+t("transform 320 MB pageable", lambda: eng.transform_cloud(Tm, rows, out=rows))
+pr = torch.from_numpy(rows).pin_memory()
+t("transform 320 MB pinned  ", lambda: eng.transform_cloud(Tm, pr, out=pr))
+dr = pr.cuda()
+t("transform 320 MB device  ", lambda: eng.transform_cloud(Tm, dr, out=dr))
