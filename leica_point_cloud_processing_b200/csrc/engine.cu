@@ -1451,7 +1451,7 @@ int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int i
     transform_to_state(transform, x);
     if (which == 1 && !c->pairs_valid) run_correspondences(c, transform, true);
     if (which == 2) c->io_b.reserve((size_t)n * 8);
-    const int64_t before = g_launch_count;
+    const int64_t before = g_launch_count.load();
     float total = 0.f;
     for (int it = 0; it < iters; ++it) {
       if (which == 0 || which == 3) {
@@ -1482,11 +1482,11 @@ int gicpb_bench_kernel(gicpb_ctx* c, int which, const float transform[16], int i
       total += ms;
     }
     *ms_mean = total / iters;
-    if (launches) *launches = g_launch_count - before;
+    if (launches) *launches = g_launch_count.load() - before;
   });
 }
 
-int64_t gicpb_launch_count(const gicpb_ctx*) { return g_launch_count; }
+int64_t gicpb_launch_count(const gicpb_ctx*) { return g_launch_count.load(); }
 
 void* gicpb_stream(const gicpb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 

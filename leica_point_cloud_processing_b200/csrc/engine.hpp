@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -30,7 +31,7 @@ struct StateError : std::runtime_error {
                                ":" + std::to_string(__LINE__) + ")");                                 \
   } while (0)
 
-extern int64_t g_launch_count;  // kernels launched by this library (all contexts)
+extern std::atomic<int64_t> g_launch_count;  // kernels launched by this library (all contexts, any host thread)
 #define GICPB_LAUNCHED()                 \
   do {                                   \
     ++::gicpb::g_launch_count;           \

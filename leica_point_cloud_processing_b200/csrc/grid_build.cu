@@ -20,7 +20,7 @@
 
 namespace gicpb {
 
-int64_t g_launch_count = 0;
+std::atomic<int64_t> g_launch_count{0};
 
 namespace {
 
