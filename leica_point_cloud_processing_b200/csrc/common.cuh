@@ -94,6 +94,8 @@ struct GridView {
   const int* pos_of;             // [n_points] original index -> position in pts (-1 for a non-finite point)
   const unsigned long long* sb_mask;  // [nsx*nsy*nsz] occupancy of the 4x4x4 bricks of a superbrick, bit (lz<<4)|(ly<<2)|lx
   const unsigned long long* hb_mask;  // [nhx*nhy*nhz] occupancy of the 4x4x4 superbricks of a hyperbrick
+  const float* brick_plane;      // [n_slots*5] or null: unit direction n of the brick's points (their PCA normal) and the
+                                 // smallest / largest n.p over them: every point of the brick lies in that slab
   float ox, oy, oz;              // origin (min corner of cell (0,0,0))
   float h, inv_h;                // cell edge and its reciprocal
   float margin;                  // conservative slack (metres) for all box-distance lower bounds
@@ -260,7 +262,19 @@ GICPB_HD bool visit_shell(const GridView& g, const Query& q, int R, V& v) {
   return false;
 }
 
-// one occupied brick: slabs (8x8x1 cells) and rows (8x1x1) nearest first, each pruned by its box distance
+// n.p exactly as the index build evaluates it for the points of a brick (same operations, same order)
+GICPB_HD float plane_dot(float nx, float ny, float nz, float x, float y, float z) {
+  return fadd(fadd(fmul(nx, x), fmul(ny, y)), fmul(nz, z));
+}
+GICPB_HD float fabs1(float v) { return v < 0.f ? -v : v; }
+
+// one occupied brick: slabs (8x8x1 cells) and rows (8x1x1) nearest first, each pruned by its box distance.
+//
+// Oriented slab of the brick (g.brick_plane): its points satisfy a <= n.p <= b.  Split q - p = alpha n + w, w normal to n:
+// |alpha| >= s (the distance from q to the slab) and, per axis i, |q_i - p_i| <= |alpha| |n_i| + |w_i|, so a box whose
+// axis gaps are g_i holds no point closer than s^2 + sum_i max(g_i - A |n_i|, 0)^2, A = the largest |alpha| the slab
+// allows.  For a query far off a thin sheet this keeps only the boxes NEAR THE FOOT of the query on the sheet, where the
+// plain box distance keeps every box within sqrt(2 R h) of it (R = distance of the query, h = box edge).
 template <class V>
 GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int bz, int slot, V& v) {
   const uint32_t* cs = g.cell_start + (size_t)slot * kBrickCells;
@@ -269,6 +283,24 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
   const float gyb = node_gap(q.y, g.oy, by, hb, g.margin);
   const float gx2 = fmul(gx, gx);
   const float gxy2 = fadd(gx2, fmul(gyb, gyb));
+  float slab2 = 0.f, anx = 0.f, any = 0.f, anz = 0.f;  // s^2 and A |n_i| (zero: the slab tests below never reject)
+  const bool slab = g.brick_plane != nullptr;
+  if (slab) {
+    const float* pl = g.brick_plane + 5 * (size_t)slot;
+    const float nx = ldg(&pl[0]), ny = ldg(&pl[1]), nz = ldg(&pl[2]), lo = ldg(&pl[3]), hi = ldg(&pl[4]);
+    const float nq = plane_dot(nx, ny, nz, q.x, q.y, q.z);
+    // the margin covers the rounding of both dot products and |n| = 1 +- 1e-7
+    const float s = fmax2(fsub(fmax2(fsub(nq, hi), fsub(lo, nq)), g.margin), 0.f);
+    const float amax = fadd(fmul(fmax2(fabs1(fsub(nq, lo)), fabs1(fsub(nq, hi))), 1.000001f), g.margin);
+    slab2 = fmul(fmul(s, s), 0.999998f);
+    anx = fmul(amax, fabs1(nx));
+    any = fmul(amax, fabs1(ny));
+    anz = fmul(amax, fabs1(nz));
+    const float gzb = node_gap(q.z, g.oz, bz, hb, g.margin);
+    const float lx = fmax2(fsub(gx, anx), 0.f), ly = fmax2(fsub(gyb, any), 0.f), lz = fmax2(fsub(gzb, anz), 0.f);
+    if (fadd(slab2, sq3(lx, ly, lz)) > v.bound()) return false;
+  }
+  const float lxb = fmax2(fsub(gx, anx), 0.f), lxb2 = fmul(lxb, lxb);
   const int zc = clampi(q.cz - (bz << 3), 0, 7), yc = clampi(q.cy - (by << 3), 0, 7);
   for (int kz = 0; kz < 8; ++kz) {
     const int lz = (zc + kz <= 7) ? zc + kz : 7 - kz;
@@ -277,6 +309,12 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
     const float gz = node_gap(q.z, g.oz, (bz << 3) + lz, h, g.margin);
     const float gz2 = fmul(gz, gz);
     if (fadd(gxy2, gz2) > v.bound()) continue;
+    const float lzs = fmax2(fsub(gz, anz), 0.f);
+    const float slz2 = fadd(slab2, fmul(lzs, lzs));  // s^2 + the z term of this slab of cells
+    if (slab) {
+      const float lys = fmax2(fsub(gyb, any), 0.f);
+      if (fadd(slz2, fadd(lxb2, fmul(lys, lys))) > v.bound()) continue;
+    }
     for (int ky = 0; ky < 8; ++ky) {
       const int ly = (yc + ky <= 7) ? yc + ky : 7 - ky;
       const unsigned rb = ldg(&cs[(lz << 6) + (ly << 3)]), re = ldg(&cs[(lz << 6) + (ly << 3) + 8]);
@@ -285,9 +323,19 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
       const float gyz2 = fadd(fmul(gy, gy), gz2);
       const float bnd = v.bound();
       if (fadd(gx2, gyz2) > bnd) continue;
+      float cut = gyz2, widen = 0.f;  // the chord of the ball in x: |q.x - p.x| <= sqrt(bnd - cut) + widen
+      if (slab) {
+        const float lyr = fmax2(fsub(gy, any), 0.f);
+        const float sl2 = fadd(slz2, fmul(lyr, lyr));
+        if (fadd(sl2, lxb2) > bnd) continue;
+        if (sl2 > gyz2 && anx < fmul(0.25f, h)) {  // the slab bound is the tighter one and widens the run by < a cell
+          cut = sl2;
+          widen = anx;
+        }
+      }
       unsigned b = rb, e = re;
       if (bnd < 3.0e38f) {  // cut the row to the chord of the ball at this (y, z)
-        const float rx = fadd(sqrt_up(fmax2(fsub(bnd, gyz2), 0.f)), g.margin);
+        const float rx = fadd(fadd(sqrt_up(fmax2(fsub(bnd, cut), 0.f)), widen), g.margin);
         const int xa = imax2(cell_of(fsub(q.x, rx), g.ox, g.inv_h) - (bx << 3), 0);
         const int xb = imin2(cell_of(fadd(q.x, rx), g.ox, g.inv_h) - (bx << 3), 7);
         if (xa > xb) continue;

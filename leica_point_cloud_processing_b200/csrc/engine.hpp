@@ -112,6 +112,7 @@ class GridIndex {
   DevBuf<uint32_t> cell_start_;
   DevBuf<int> pos_of_;
   DevBuf<unsigned long long> sb_mask_, hb_mask_;
+  DevBuf<float> brick_plane_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
   unsigned* h_pin_ = nullptr; // pinned host words the build reads its counters back into
 };

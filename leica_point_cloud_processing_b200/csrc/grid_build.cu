@@ -243,6 +243,85 @@ inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + thre
 
 }  // namespace
 
+// Oriented slab of every occupied brick (GridView::brick_plane, used by visit_brick): one warp per brick slot.  The
+// direction is the eigenvector of the smallest eigenvalue of the covariance of the brick's points (any unit vector would
+// be valid; this one makes the slab thin for a sheet); lo / hi are the extremes of plane_dot(n, p) over the brick's
+// points, evaluated exactly as the search evaluates it for a query.
+__device__ __forceinline__ void jacobi3(double (&a)[9], double (&v)[9], int p, int q) {
+  const double apq = a[3 * p + q];
+  if (apq == 0.0) return;
+  const double theta = (a[3 * q + q] - a[3 * p + p]) / (2.0 * apq);
+  const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+  for (int k = 0; k < 3; ++k) {
+    const double akp = a[3 * k + p], akq = a[3 * k + q];
+    a[3 * k + p] = c * akp - s * akq;
+    a[3 * k + q] = s * akp + c * akq;
+  }
+  for (int k = 0; k < 3; ++k) {
+    const double apk = a[3 * p + k], aqk = a[3 * q + k];
+    a[3 * p + k] = c * apk - s * aqk;
+    a[3 * q + k] = s * apk + c * aqk;
+  }
+  for (int k = 0; k < 3; ++k) {
+    const double vkp = v[3 * k + p], vkq = v[3 * k + q];
+    v[3 * k + p] = c * vkp - s * vkq;
+    v[3 * k + q] = s * vkp + c * vkq;
+  }
+}
+
+__global__ void __launch_bounds__(128) brick_plane_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+                                                           int n_slots, float* __restrict__ plane) {
+  const int slot = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (slot >= n_slots) return;
+  const unsigned b = cell_start[(size_t)slot * kBrickCells], e = cell_start[(size_t)(slot + 1) * kBrickCells];
+  // moments about the brick's first point (keeps the sums small), in double, fixed order
+  const float4 p0 = pts[b];
+  double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
+  for (unsigned i = b + lane; i < e; i += 32) {
+    const float4 p = pts[i];
+    const double x = (double)p.x - (double)p0.x, y = (double)p.y - (double)p0.y, z = (double)p.z - (double)p0.z;
+    sm[0] += x; sm[1] += y; sm[2] += z;
+    sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sm[k] = warp_sum(sm[k]);
+  const double m = (double)(e - b);
+  const double mx = sm[0] / m, my = sm[1] / m, mz = sm[2] / m;
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  a[0] = sm[3] / m - mx * mx; a[1] = sm[4] / m - mx * my; a[2] = sm[5] / m - mx * mz;
+  a[4] = sm[6] / m - my * my; a[5] = sm[7] / m - my * mz; a[8] = sm[8] / m - mz * mz;
+  a[3] = a[1]; a[6] = a[2]; a[7] = a[5];
+  for (int sweep = 0; sweep < 24; ++sweep) {  // every lane runs the same arithmetic on the same sums
+    const double off = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
+    if (off == 0.0 || off < 1e-20 * (fabs(a[0]) + fabs(a[4]) + fabs(a[8]))) break;
+    jacobi3(a, v, 0, 1);
+    jacobi3(a, v, 0, 2);
+    jacobi3(a, v, 1, 2);
+  }
+  int best = 0;
+  if (fabs(a[4]) < fabs(a[0])) best = 1;
+  if (fabs(a[8]) < fabs(a[4 * best])) best = 2;
+  float nx = (float)v[best], ny = (float)v[3 + best], nz = (float)v[6 + best];
+  if (!(fabsf(nx) + fabsf(ny) + fabsf(nz) > 0.5f)) { nx = 0.f; ny = 0.f; nz = 1.f; }  // degenerate input: any direction will do
+  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+  for (unsigned i = b + lane; i < e; i += 32) {
+    const float4 p = pts[i];
+    const float d = plane_dot(nx, ny, nz, p.x, p.y, p.z);
+    lo = fminf(lo, d);
+    hi = fmaxf(hi, d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(kFullMask, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(kFullMask, hi, o));
+  }
+  if (lane == 0) {
+    float* out = plane + 5 * (size_t)slot;
+    out[0] = nx; out[1] = ny; out[2] = nz; out[3] = lo; out[4] = hi;
+  }
+}
+
 // Ask for the largest shared-memory carve-out on every index-build kernel so that their blocks can share an SM with the
 // kNN kernel (which needs it) when both run on different streams (gicpb_set_clouds).
 void prefer_shared_carveout_grid() {
@@ -256,6 +335,7 @@ void prefer_shared_carveout_grid() {
   cudaFuncSetAttribute(brick_flags_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(brick_slots_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(cell_start_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(brick_plane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   (void)cudaGetLastError();
 }
 
@@ -441,10 +521,15 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   cell_start_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, cell_start_.get(),
                                                                    scratch_.get());
   GICPB_LAUNCHED();
+  brick_plane_.reserve((size_t)n_slots * 5);
+  brick_plane_kernel<<<blocks_for(n_slots * 32, 128), 128, 0, stream>>>(pts_sorted_.get(), cell_start_.get(), (int)n_slots,
+                                                                        brick_plane_.get());
+  GICPB_LAUNCHED();
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
 
   g.pts = pts_sorted_.get();
+  g.brick_plane = brick_plane_.get();
   g.brick_slot = brick_slot_.get();
   g.cell_start = cell_start_.get();
   g.pos_of = pos_of_.get();

@@ -22,6 +22,7 @@ struct HostIndex {
   std::vector<uint32_t> cell_start;
   std::vector<unsigned long long> sb, hb;
   std::vector<int> pos_of;
+  std::vector<float> plane;
   GridView g{};
 };
 
@@ -105,6 +106,49 @@ static void build_index(const std::vector<float3>& in, float h, HostIndex& ix) {
   g.pos_of = ix.pos_of.data();
   g.sb_mask = ix.sb.data();
   g.hb_mask = ix.hb.data();
+  // oriented slab per brick, as brick_plane_kernel builds it: PCA normal, extremes of plane_dot over the brick's points.
+  // Every third brick gets an arbitrary (non-normal) direction instead: any direction must leave the search exact.
+  ix.plane.assign((size_t)n_slots * 5, 0.f);
+  std::vector<double> acc((size_t)n_slots * 10, 0.0);
+  for (int i = 0; i < n; ++i) {
+    double* a = &acc[(size_t)slot_of[i] * 10];
+    const float4& p = ix.pts[i];
+    a[0] += 1; a[1] += p.x; a[2] += p.y; a[3] += p.z;
+    a[4] += (double)p.x * p.x; a[5] += (double)p.x * p.y; a[6] += (double)p.x * p.z;
+    a[7] += (double)p.y * p.y; a[8] += (double)p.y * p.z; a[9] += (double)p.z * p.z;
+  }
+  for (int sl = 0; sl < n_slots; ++sl) {
+    const double* a = &acc[(size_t)sl * 10];
+    const double m = a[0], mx = a[1] / m, my = a[2] / m, mz = a[3] / m;
+    double A[3][3] = {{a[4] / m - mx * mx, a[5] / m - mx * my, a[6] / m - mx * mz}, {0, a[7] / m - my * my, a[8] / m - my * mz}, {0, 0, a[9] / m - mz * mz}};
+    A[1][0] = A[0][1]; A[2][0] = A[0][2]; A[2][1] = A[1][2];
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 30; ++sweep)
+      for (int p = 0; p < 2; ++p)
+        for (int q2 = p + 1; q2 < 3; ++q2) {
+          if (std::fabs(A[p][q2]) < 1e-300) continue;
+          const double th = (A[q2][q2] - A[p][p]) / (2 * A[p][q2]);
+          const double tt = (th >= 0 ? 1 : -1) / (std::fabs(th) + std::sqrt(th * th + 1));
+          const double c = 1 / std::sqrt(tt * tt + 1), s2 = tt * c;
+          for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q2]; A[k][p] = c * akp - s2 * akq; A[k][q2] = s2 * akp + c * akq; }
+          for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q2][k]; A[p][k] = c * apk - s2 * aqk; A[q2][k] = s2 * apk + c * aqk; }
+          for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q2]; V[k][p] = c * vkp - s2 * vkq; V[k][q2] = s2 * vkp + c * vkq; }
+        }
+    int best = 0;
+    for (int k = 1; k < 3; ++k) if (std::fabs(A[k][k]) < std::fabs(A[best][best])) best = k;
+    float* pl = &ix.plane[(size_t)sl * 5];
+    pl[0] = (float)V[0][best]; pl[1] = (float)V[1][best]; pl[2] = (float)V[2][best];
+    if (sl % 3 == 1) { pl[0] = 0.6f; pl[1] = -0.48f; pl[2] = 0.64f; }
+    if (!(std::fabs(pl[0]) + std::fabs(pl[1]) + std::fabs(pl[2]) > 0.5f)) { pl[0] = 0; pl[1] = 0; pl[2] = 1; }
+    pl[3] = inf(); pl[4] = -inf();
+  }
+  for (int i = 0; i < n; ++i) {
+    float* pl = &ix.plane[(size_t)slot_of[i] * 5];
+    const float4& p = ix.pts[i];
+    const float d = plane_dot(pl[0], pl[1], pl[2], p.x, p.y, p.z);
+    pl[3] = std::min(pl[3], d); pl[4] = std::max(pl[4], d);
+  }
+  g.brick_plane = ix.plane.data();
 }
 
 static long g_fail = 0, g_checks = 0, g_far = 0, g_knn_far = 0;
