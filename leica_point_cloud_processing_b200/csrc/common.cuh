@@ -268,13 +268,21 @@ GICPB_HD float plane_dot(float nx, float ny, float nz, float x, float y, float z
 }
 GICPB_HD float fabs1(float v) { return v < 0.f ? -v : v; }
 
+// lower bound of |f - p| along one axis for f anywhere in [flo, fhi] and p in the box [lo, lo + size); never negative
+GICPB_HD float interval_gap(float flo, float fhi, float lo, float size, float margin) {
+  const float d = fmax2(fsub(lo, fhi), fsub(flo, fadd(lo, size)));
+  return fmax2(fsub(d, margin), 0.0f);
+}
+
 // one occupied brick: slabs (8x8x1 cells) and rows (8x1x1) nearest first, each pruned by its box distance.
 //
-// Oriented slab of the brick (g.brick_plane): its points satisfy a <= n.p <= b.  Split q - p = alpha n + w, w normal to n:
-// |alpha| >= s (the distance from q to the slab) and, per axis i, |q_i - p_i| <= |alpha| |n_i| + |w_i|, so a box whose
-// axis gaps are g_i holds no point closer than s^2 + sum_i max(g_i - A |n_i|, 0)^2, A = the largest |alpha| the slab
-// allows.  For a query far off a thin sheet this keeps only the boxes NEAR THE FOOT of the query on the sheet, where the
-// plain box distance keeps every box within sqrt(2 R h) of it (R = distance of the query, h = box edge).
+// Oriented slab of the brick (g.brick_plane): its points satisfy lo <= n.p <= hi.  Split q - p = alpha n + w, w normal
+// to n.  Then alpha = n.q - n.p lies in [n.q - hi, n.q - lo], |alpha| >= s (the distance from n.q to [lo, hi]), and per
+// axis i   p_i = (q_i - alpha n_i) - w_i:   the point sits within |w_i| of the FOOT interval F_i = q_i - n_i [alpha range]
+// (where the query lands on the slab along n).  A box whose interval on axis i is l_i away from F_i therefore holds no
+// point closer than s^2 + sum_i l_i^2.  For a query far off a thin sheet F is as small as the sheet is thin, so only the
+// boxes NEAR THE FOOT of the query are opened, where the plain box distance keeps every box within sqrt(2 R h) of the
+// touch point (R = distance of the query, h = box edge).  Any direction n keeps the search exact.
 template <class V>
 GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int bz, int slot, V& v) {
   const uint32_t* cs = g.cell_start + (size_t)slot * kBrickCells;
@@ -283,24 +291,28 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
   const float gyb = node_gap(q.y, g.oy, by, hb, g.margin);
   const float gx2 = fmul(gx, gx);
   const float gxy2 = fadd(gx2, fmul(gyb, gyb));
-  float slab2 = 0.f, anx = 0.f, any = 0.f, anz = 0.f;  // s^2 and A |n_i| (zero: the slab tests below never reject)
   const bool slab = g.brick_plane != nullptr;
+  float slab2 = 0.f;                                                         // s^2
+  float fxl = q.x, fxh = q.x, fyl = q.y, fyh = q.y, fzl = q.z, fzh = q.z;  // foot intervals
+  float lxb2 = gx2, lyb = gyb;                                               // foot-to-brick gaps in x (squared) and y
   if (slab) {
     const float* pl = g.brick_plane + 5 * (size_t)slot;
     const float nx = ldg(&pl[0]), ny = ldg(&pl[1]), nz = ldg(&pl[2]), lo = ldg(&pl[3]), hi = ldg(&pl[4]);
     const float nq = plane_dot(nx, ny, nz, q.x, q.y, q.z);
     // the margin covers the rounding of both dot products and |n| = 1 +- 1e-7
     const float s = fmax2(fsub(fmax2(fsub(nq, hi), fsub(lo, nq)), g.margin), 0.f);
-    const float amax = fadd(fmul(fmax2(fabs1(fsub(nq, lo)), fabs1(fsub(nq, hi))), 1.000001f), g.margin);
     slab2 = fmul(fmul(s, s), 0.999998f);
-    anx = fmul(amax, fabs1(nx));
-    any = fmul(amax, fabs1(ny));
-    anz = fmul(amax, fabs1(nz));
-    const float gzb = node_gap(q.z, g.oz, bz, hb, g.margin);
-    const float lx = fmax2(fsub(gx, anx), 0.f), ly = fmax2(fsub(gyb, any), 0.f), lz = fmax2(fsub(gzb, anz), 0.f);
-    if (fadd(slab2, sq3(lx, ly, lz)) > v.bound()) return false;
+    const float al = fsub(fsub(nq, hi), g.margin), ah = fadd(fsub(nq, lo), g.margin);  // alpha range, widened
+    const float x0 = fmul(nx, al), x1 = fmul(nx, ah), y0 = fmul(ny, al), y1 = fmul(ny, ah), z0 = fmul(nz, al), z1 = fmul(nz, ah);
+    fxl = fsub(q.x, fmax2(x0, x1)); fxh = fsub(q.x, fmin2(x0, x1));
+    fyl = fsub(q.y, fmax2(y0, y1)); fyh = fsub(q.y, fmin2(y0, y1));
+    fzl = fsub(q.z, fmax2(z0, z1)); fzh = fsub(q.z, fmin2(z0, z1));
+    const float lx = interval_gap(fxl, fxh, fadd(g.ox, fmul((float)bx, hb)), hb, g.margin);
+    lyb = interval_gap(fyl, fyh, fadd(g.oy, fmul((float)by, hb)), hb, g.margin);
+    const float lzb = interval_gap(fzl, fzh, fadd(g.oz, fmul((float)bz, hb)), hb, g.margin);
+    lxb2 = fmul(lx, lx);
+    if (fadd(slab2, fadd(lxb2, fadd(fmul(lyb, lyb), fmul(lzb, lzb)))) > v.bound()) return false;
   }
-  const float lxb = fmax2(fsub(gx, anx), 0.f), lxb2 = fmul(lxb, lxb);
   const int zc = clampi(q.cz - (bz << 3), 0, 7), yc = clampi(q.cy - (by << 3), 0, 7);
   for (int kz = 0; kz < 8; ++kz) {
     const int lz = (zc + kz <= 7) ? zc + kz : 7 - kz;
@@ -309,11 +321,11 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
     const float gz = node_gap(q.z, g.oz, (bz << 3) + lz, h, g.margin);
     const float gz2 = fmul(gz, gz);
     if (fadd(gxy2, gz2) > v.bound()) continue;
-    const float lzs = fmax2(fsub(gz, anz), 0.f);
-    const float slz2 = fadd(slab2, fmul(lzs, lzs));  // s^2 + the z term of this slab of cells
+    float slz2 = gz2;  // s^2 + the foot-to-cells gap in z, squared
     if (slab) {
-      const float lys = fmax2(fsub(gyb, any), 0.f);
-      if (fadd(slz2, fadd(lxb2, fmul(lys, lys))) > v.bound()) continue;
+      const float lzs = interval_gap(fzl, fzh, fadd(g.oz, fmul((float)((bz << 3) + lz), h)), h, g.margin);
+      slz2 = fadd(slab2, fmul(lzs, lzs));
+      if (fadd(slz2, fadd(lxb2, fmul(lyb, lyb))) > v.bound()) continue;
     }
     for (int ky = 0; ky < 8; ++ky) {
       const int ly = (yc + ky <= 7) ? yc + ky : 7 - ky;
@@ -323,21 +335,23 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
       const float gyz2 = fadd(fmul(gy, gy), gz2);
       const float bnd = v.bound();
       if (fadd(gx2, gyz2) > bnd) continue;
-      float cut = gyz2, widen = 0.f;  // the chord of the ball in x: |q.x - p.x| <= sqrt(bnd - cut) + widen
+      float sl2 = 0.f;
       if (slab) {
-        const float lyr = fmax2(fsub(gy, any), 0.f);
-        const float sl2 = fadd(slz2, fmul(lyr, lyr));
+        const float lyr = interval_gap(fyl, fyh, fadd(g.oy, fmul((float)((by << 3) + ly), h)), h, g.margin);
+        sl2 = fadd(slz2, fmul(lyr, lyr));
         if (fadd(sl2, lxb2) > bnd) continue;
-        if (sl2 > gyz2 && anx < fmul(0.25f, h)) {  // the slab bound is the tighter one and widens the run by < a cell
-          cut = sl2;
-          widen = anx;
-        }
       }
       unsigned b = rb, e = re;
-      if (bnd < 3.0e38f) {  // cut the row to the chord of the ball at this (y, z)
-        const float rx = fadd(fadd(sqrt_up(fmax2(fsub(bnd, cut), 0.f)), widen), g.margin);
-        const int xa = imax2(cell_of(fsub(q.x, rx), g.ox, g.inv_h) - (bx << 3), 0);
-        const int xb = imin2(cell_of(fadd(q.x, rx), g.ox, g.inv_h) - (bx << 3), 7);
+      if (bnd < 3.0e38f) {  // cut the row to the chord of the ball at this (y, z), and to the reach of the foot interval
+        const float rx = fadd(sqrt_up(fmax2(fsub(bnd, gyz2), 0.f)), g.margin);
+        float xlo = fsub(q.x, rx), xhi = fadd(q.x, rx);
+        if (slab) {
+          const float rw = fadd(sqrt_up(fmax2(fsub(bnd, sl2), 0.f)), g.margin);
+          xlo = fmax2(xlo, fsub(fxl, rw));
+          xhi = fmin2(xhi, fadd(fxh, rw));
+        }
+        const int xa = imax2(cell_of(xlo, g.ox, g.inv_h) - (bx << 3), 0);
+        const int xb = imin2(cell_of(xhi, g.ox, g.inv_h) - (bx << 3), 7);
         if (xa > xb) continue;
         if (xa > 0) b = ldg(&cs[(lz << 6) + (ly << 3) + xa]);
         if (xb < 7) e = ldg(&cs[(lz << 6) + (ly << 3) + xb + 1]);
