@@ -314,8 +314,16 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
     if (fadd(slab2, fadd(lxb2, fadd(fmul(lyb, lyb), fmul(lzb, lzb)))) > v.bound()) return false;
   }
   const int zc = clampi(q.cz - (bz << 3), 0, 7), yc = clampi(q.cy - (by << 3), 0, 7);
+  // layers of cells the foot interval can reach in z under the bound on entry (a later, smaller bound only narrows it)
+  int za = 0, zb = 7;
+  if (slab && v.bound() < 3.0e38f) {
+    const float rz = fadd(sqrt_up(fmax2(fsub(fsub(v.bound(), slab2), fadd(lxb2, fmul(lyb, lyb))), 0.f)), g.margin);
+    za = imax2(cell_of(fsub(fzl, rz), g.oz, g.inv_h) - (bz << 3), 0);
+    zb = imin2(cell_of(fadd(fzh, rz), g.oz, g.inv_h) - (bz << 3), 7);
+  }
   for (int kz = 0; kz < 8; ++kz) {
     const int lz = (zc + kz <= 7) ? zc + kz : 7 - kz;
+    if (lz < za || lz > zb) continue;
     const unsigned sb = ldg(&cs[lz << 6]), se = ldg(&cs[(lz << 6) + 64]);
     if (sb == se) continue;
     const float gz = node_gap(q.z, g.oz, (bz << 3) + lz, h, g.margin);
@@ -327,8 +335,15 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
       slz2 = fadd(slab2, fmul(lzs, lzs));
       if (fadd(slz2, fadd(lxb2, fmul(lyb, lyb))) > v.bound()) continue;
     }
+    int ya = 0, yb = 7;  // rows of this layer the foot interval can reach in y
+    if (slab && v.bound() < 3.0e38f) {
+      const float ry = fadd(sqrt_up(fmax2(fsub(fsub(v.bound(), slz2), lxb2), 0.f)), g.margin);
+      ya = imax2(cell_of(fsub(fyl, ry), g.oy, g.inv_h) - (by << 3), 0);
+      yb = imin2(cell_of(fadd(fyh, ry), g.oy, g.inv_h) - (by << 3), 7);
+    }
     for (int ky = 0; ky < 8; ++ky) {
       const int ly = (yc + ky <= 7) ? yc + ky : 7 - ky;
+      if (ly < ya || ly > yb) continue;
       const unsigned rb = ldg(&cs[(lz << 6) + (ly << 3)]), re = ldg(&cs[(lz << 6) + (ly << 3) + 8]);
       if (rb == re) continue;
       const float gy = node_gap(q.y, g.oy, (by << 3) + ly, h, g.margin);
