@@ -113,6 +113,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is the CPU implementation "with all the host threads it
+    # can use", so the OpenMP runtime of the oracle library (loaded below, not before) gets the whole host back
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle.oracle import Oracle, default_params
     orc = Oracle(fast=True)
     n_full = workload_points(args.gpus, args.points)
