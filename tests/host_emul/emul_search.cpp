@@ -220,7 +220,7 @@ int main(int argc, char** argv) {
   std::mt19937 rng(12345);
   std::uniform_real_distribution<float> U(0.f, 1.f);
   std::normal_distribution<float> N(0.f, 1.f);
-  for (int scenario = 0; scenario < 7; ++scenario) {
+  for (int scenario = 0; scenario < 9; ++scenario) {
     std::vector<float3> pts;
     float h = 0.05f;
     const char* name = "";
@@ -252,6 +252,20 @@ int main(int argc, char** argv) {
       for (int i = 0; i < 300; ++i) pts.push_back({1.f, 2.f, 3.f});
       for (int i = 0; i < 40; ++i) pts.push_back({1.f + U(rng), 2.f, 3.f});
       h = 0.01f;
+    } else if (scenario == 7) {  // thin sheet tilted against all three axes: the regime of the oriented brick slabs
+      name = "tilted sheet";
+      for (int i = 0; i < 30000; ++i) {
+        const float a = U(rng) * 3 - 1.5f, b = U(rng) * 2 - 1.0f;
+        pts.push_back({a + 0.31f * b, 0.93f * b - 0.2f * a, 0.37f * a + 0.29f * b + 0.0002f * N(rng)});
+      }
+      h = 0.02f;
+    } else if (scenario == 8) {  // two parallel sheets 3 cells apart plus a step: slabs that are NOT thin
+      name = "double sheet";
+      for (int i = 0; i < 30000; ++i) {
+        const float a = U(rng) * 2, b = U(rng) * 2;
+        pts.push_back({a, b, (i & 1 ? 0.06f : 0.0f) + (a > 1.0f ? 0.15f : 0.0f) + 0.0005f * N(rng)});
+      }
+      h = 0.02f;
     } else {  // cube faces (reference fixture shape), coarse cells
       name = "cube";
       for (int i = 0; i < 5000; ++i) {

@@ -17,3 +17,8 @@ def test_traversal_matches_brute_force(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "0 failures" in out.stdout
+    # again with EVERY query answered by the hierarchical far traversal alone (oriented brick slabs, a third of them with
+    # an arbitrary direction; thin tilted sheets and thick double sheets among the point sets)
+    out = subprocess.run([exe, "far"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert "0 failures" in out.stdout
