@@ -268,6 +268,15 @@ GICPB_HD float plane_dot(float nx, float ny, float nz, float x, float y, float z
 }
 GICPB_HD float fabs1(float v) { return v < 0.f ? -v : v; }
 
+// A visitor for which seeing a point twice is harmless (a running minimum) declares `static constexpr bool kRescanOk =
+// true`; visit_brick then looks at the cell under the query's foot first.  Visitors that collect (kNN) or count do not.
+template <class V>
+GICPB_HD constexpr auto rescan_ok_impl(int) -> decltype(V::kRescanOk) { return V::kRescanOk; }
+template <class V>
+GICPB_HD constexpr bool rescan_ok_impl(long) { return false; }
+template <class V>
+GICPB_HD constexpr bool rescan_ok() { return rescan_ok_impl<V>(0); }
+
 // lower bound of |f - p| along one axis for f anywhere in [flo, fhi] and p in the box [lo, lo + size); never negative
 GICPB_HD float interval_gap(float flo, float fhi, float lo, float size, float margin) {
   const float d = fmax2(fsub(lo, fhi), fsub(flo, fadd(lo, size)));
@@ -312,6 +321,17 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
     const float lzb = interval_gap(fzl, fzh, fadd(g.oz, fmul((float)bz, hb)), hb, g.margin);
     lxb2 = fmul(lx, lx);
     if (fadd(slab2, fadd(lxb2, fadd(fmul(lyb, lyb), fmul(lzb, lzb)))) > v.bound()) return false;
+  }
+  if (slab && rescan_ok<V>()) {
+    // The nearest point of a thin sheet lies next to the query's foot on it: the cell under the foot is scanned first, so
+    // that the layers and rows below are already cut with a bound within a cell of the final one (counted on the host
+    // build: point tests per far query 142 -> 105, row tests 25 -> 17).  Its points are seen again in their row.
+    const int fx = clampi(cell_of(fmul(0.5f, fadd(fxl, fxh)), g.ox, g.inv_h) - (bx << 3), 0, 7);
+    const int fy = clampi(cell_of(fmul(0.5f, fadd(fyl, fyh)), g.oy, g.inv_h) - (by << 3), 0, 7);
+    const int fz = clampi(cell_of(fmul(0.5f, fadd(fzl, fzh)), g.oz, g.inv_h) - (bz << 3), 0, 7);
+    const unsigned code = local_code((unsigned)fx, (unsigned)fy, (unsigned)fz);
+    const unsigned b0 = ldg(&cs[code]), e0 = ldg(&cs[code + 1]);
+    if (b0 < e0 && v.range(b0, e0)) return true;
   }
   const int zc = clampi(q.cz - (bz << 3), 0, 7), yc = clampi(q.cy - (by << 3), 0, 7);
   // layers of cells the foot interval can reach in z under the bound on entry (a later, smaller bound only narrows it)
@@ -493,6 +513,7 @@ struct NNState {
 
 template <bool kEarlyExit>
 struct NNVisitor {
+  static constexpr bool kRescanOk = true;  // a running minimum: a point seen twice changes nothing
   const float4* pts;
   float qx, qy, qz;
   NNState s;
