@@ -15,6 +15,10 @@
  *   - `on_device` != 0 means the pointer is a CUDA device pointer on the context's GPU; otherwise host
  *     (pinned host memory is copied as it is; pageable host clouds of 8 MB and more - a pcl::PointCloud - are gathered
  *     into packed xyz rows by a few host threads through a ring of pinned chunks, so 12 bytes per point cross PCIe)
+ *   - Device pointers (stream contract): the library launches on its own non-blocking streams and every call waits
+ *     for its work before it returns.  It does NOT order itself against the caller's streams: memory behind an
+ *     `on_device` input must be completely written, and memory behind a device output no longer in use, before the
+ *     call is made (synchronise the producing stream, or make gicpb_stream(ctx) wait on an event of it)
  *   - 4x4 transforms are float32, ROW-major (T[4*r + c]); Eigen::Matrix4f is column-major, the shim transposes
  *   - a context is bound to one GPU and is not thread-safe; distinct contexts are independent
  *   - there is no CPU fallback: without a usable GPU gicpb_create fails with GICPB_E_CUDA

@@ -194,6 +194,15 @@ def find_libnccl():
     return None
 
 
+def _sync_producer(t):
+    """The engine launches on its own non-blocking streams (include/gicp_b200.h, "Device pointers"): whatever torch has
+    queued on its current stream for this tensor (a clone, an index_select, a kernel that writes it) must be complete
+    before the engine reads or overwrites the memory.  Every engine call waits for its own work before it returns, so
+    this one-sided wait orders both directions."""
+    import torch
+    torch.cuda.current_stream(t.device).synchronize()
+
+
 def _as_cloud(a):
     """Return (keepalive, pointer, n, stride_bytes, on_device) for a numpy array [n, >=3] float32 (any row stride),
     a structured/byte numpy array of 32-byte points, or a CUDA torch tensor [n, 3|4|8] float32."""
@@ -202,6 +211,8 @@ def _as_cloud(a):
             raise TypeError("cloud tensor must be float32")
         if a.dim() != 2 or a.shape[1] < 3 or a.stride(1) != 1:
             raise TypeError("cloud tensor must be [n, >=3] with unit inner stride")
+        if a.is_cuda:
+            _sync_producer(a)
         return a, a.data_ptr(), int(a.shape[0]), int(a.stride(0)) * 4, 1 if a.is_cuda else 0
     a = np.asarray(a)
     if a.dtype != np.float32:
@@ -346,7 +357,11 @@ class Engine:
         Tk, Tp = _T(T)
         keep, ptr, n, stride, dev = _as_cloud(cloud)
         if out is None:
-            out = keep.clone() if dev else keep.copy()
+            if dev:
+                import torch
+                out = torch.empty_like(keep)  # the kernel writes every word of every point
+            else:
+                out = keep.copy()
         okeep, optr, on, ostride, odev = _as_cloud(out)
         if (on, ostride, odev) != (n, stride, dev):
             raise ValueError("out must match the input cloud's shape, stride and device")

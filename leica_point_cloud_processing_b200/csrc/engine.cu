@@ -450,7 +450,10 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
   const bool polled = out == c->h_sums_dev;
   unsigned stamp = 0;
   if (polled) {
-    if (++c->eval_stamp == 0u || c->eval_stamp >= (1u << 30)) c->eval_stamp = 1u;
+    if (++c->eval_stamp == 0u || c->eval_stamp >= (1u << 30)) {
+      c->eval_stamp = 1u;
+      c->h_sums[15] = 0.0;  // no kernel is in flight here (every evaluation is waited for): forget the pre-wrap stamps
+    }
     stamp = c->eval_stamp;
   }
   launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32, T,
@@ -477,7 +480,10 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
     GICPB_CUDA(cudaStreamSynchronize(c->stream));
   }
   for (int i = 0; i < kCostSums; ++i) sums[i] = c->h_sums[i];
-  if (fused && std::isnan(sums[13])) throw NcclError("peer-memory reduction timed out: a rank did not launch this evaluation");
+  if (fused && std::isnan(sums[13])) {
+    c->peer_ready = false;  // the slot flags are out of step from here on: this context goes back to ncclAllReduce
+    throw NcclError("peer-memory reduction timed out: a rank did not launch this evaluation (GICPB_PEER_TIMEOUT_MS)");
+  }
   ++c->cost_evals;
 }
 
@@ -716,6 +722,7 @@ int gicpb_create(int device, gicpb_ctx** out) {
     for (auto& p : c->prefetch) GICPB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
     GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
+    std::memset(c->h_sums, 0, 16 * sizeof(double));  // h_sums[15] is polled for a stamp: recycled pinned pages may hold one
     GICPB_CUDA(cudaHostAlloc(&c->h_mom, 80 * sizeof(double), cudaHostAllocDefault));
     GICPB_CUDA(cudaHostAlloc(&c->h_far, 4 * sizeof(unsigned), cudaHostAllocDefault));
     c->ticket.reserve(4);
@@ -827,6 +834,9 @@ int gicpb_peer_import(gicpb_ctx* c, const unsigned char* handles, int world) {
     if (world != c->world || world < 2 || world > kMaxPeers) throw ArgError("world must match gicpb_comm_init (2..16)");
     if (!c->peer_own) throw StateError("gicpb_peer_export must be called first");
     c->peer_ready = false;
+    // seq restarts at 0 below: the flag words of an earlier import must not look like evaluations already done
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    GICPB_CUDA(cudaMemset(c->peer_own, 0, sizeof(PeerSlots)));
     for (int r = 0; r < world; ++r) {
       if (r == c->rank) {
         c->peer.peers[r] = c->peer_own;
@@ -841,6 +851,11 @@ int gicpb_peer_import(gicpb_ctx* c, const unsigned char* handles, int world) {
     c->peer.rank = c->rank;
     c->peer.world = world;
     c->peer.seq = 0u;
+    {
+      const char* env = std::getenv("GICPB_PEER_TIMEOUT_MS");
+      const double ms = env && *env ? std::atof(env) : 30000.0;
+      c->peer.timeout_ns = (unsigned long long)(std::max(ms, 1.0) * 1e6);
+    }
     c->peer_ready = true;
   });
 }
@@ -1073,7 +1088,7 @@ int gicpb_nn1(gicpb_ctx* c, const void* queries, int64_t n, int64_t stride, int 
     c->io_b.reserve((size_t)n * 8);
     int* d_idx = reinterpret_cast<int*>(c->io_b.get());
     float* d_d2 = reinterpret_cast<float*>(c->io_b.get() + (size_t)n * 4);
-    const float gate2 = max_dist > 0 ? round_up_to_float(max_dist * max_dist) : 0.f;
+    const float gate2 = max_dist > 0 ? round_up_to_float(max_dist * max_dist) : -1.f;  // <= 0: ungated
     launch_nn1(c->tgt.view(), c->queries.get(), (int)n, T, gate2, d_idx, d_d2, nullptr, far_work(c, n), c->stream);
     if (idx) GICPB_CUDA(cudaMemcpyAsync(idx, d_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (d2) GICPB_CUDA(cudaMemcpyAsync(d2, d_d2, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -127,11 +127,12 @@ struct PeerReduce {
   PeerSlots* peers[kMaxPeers];  // peers[r] = rank r's block as mapped in this process (peers[rank] = own)
   int rank, world;
   unsigned seq;                 // evaluation counter, identical on all ranks, never 0
+  unsigned long long timeout_ns;  // how long the last block waits for the other ranks' flags (GICPB_PEER_TIMEOUT_MS, default 30 s)
 };
 // sums over this rank's pairs; `partials` holds cost_grid_blocks * kCostSums doubles, `ticket` one zeroed uint.
 // out14 may be device memory or mapped pinned host memory.
-// peer != nullptr: out14 receives the sum over all ranks (see PeerReduce); a peer that does not show up within ~2 s
-// makes every entry NaN.
+// peer != nullptr: out14 receives the sum over all ranks (see PeerReduce); a peer that does not show up within
+// PeerReduce::timeout_ns makes every entry NaN.
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                  const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream,
                  const PeerReduce* peer = nullptr, unsigned stamp = 0);

@@ -26,9 +26,11 @@ namespace {
 constexpr int kNnThreads = 128;
 constexpr int kQueueCap = 16;  // point ranges a thread can queue before it scans (3x3 rows, some split by a brick edge)
 
+// gate2 >= 0: only candidates with d2 < gate2 count (gate2 == 0 admits none, as PCL's `nn_dists[0] < dist_threshold`
+// with a zero threshold); gate2 < 0: ungated
 __device__ __forceinline__ NNState nn_init(float gate2) {
   NNState s;
-  if (gate2 > 0.f) {
+  if (gate2 >= 0.f) {
     s.best = gate2;  // strict '<' gate: nothing ties with the sentinel because its index is -1
     s.pos = -1;
     s.oi = -1;
@@ -165,7 +167,8 @@ correspondence_kernel(GridView g, const float4* __restrict__ src, int lo, int hi
       }
     }
     bool hit;
-    if (finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, t, fw, qb, qe, hit)) return;
+    // a zero gate admits no candidate: nothing to search for
+    if (gate2 != 0.f && finite3(q.x, q.y, q.z) && !search_item<kFar, false>(g, q.x, q.y, q.z, s, t, fw, qb, qe, hit)) return;
     pair_pos[t] = s.pos;
     pair_d2[t] = s.pos >= 0 ? s.best : __int_as_float(0x7f800000);
     if (s.pos < 0) {
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridV
   auto body = [&](int t) {
     const float4 p = __ldg(&src[lo + t]);
     const float3 q = xform(T, p.x, p.y, p.z);
-    NNState s = nn_init(0.f);
+    NNState s = nn_init(-1.f);
     if (seed) {
       const int prev = __ldg(&seed[t]);
       if (prev >= 0) {

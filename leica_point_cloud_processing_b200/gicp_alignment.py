@@ -47,6 +47,7 @@ class GICPAlignment:
         self._converged = False
         self._fitness = None
         self._inputs_set = False
+        self._input_source_ = None
         self.last_result = None
 
     # ---- public surface (include/GICPAlignment.h:63-145) ---------------------------------------------
@@ -82,12 +83,13 @@ class GICPAlignment:
         self.aligned_cloud_ = self._engine.transform_cloud(self.fine_tf_, cloud)
 
     def setSourceCloud(self, source_cloud):
+        # reference :166-169: only the wrapper's pointer changes.  gicp_ keeps the cloud it was given by
+        # setInputSource in fineAlignment (:89), so a following iterate() still solves on the OLD pair; the new cloud
+        # is used from the next run() on
         self.source_cloud_ = source_cloud
-        self._inputs_set = False
 
     def setTargetCloud(self, target_cloud):
-        self.target_cloud_ = target_cloud
-        self._inputs_set = False
+        self.target_cloud_ = target_cloud  # reference :171-174, same remark
 
     def setMaxIterations(self, iterations):
         self.max_iter_ = int(iterations)
@@ -162,6 +164,7 @@ class GICPAlignment:
         self._engine.prefetch(1, self.source_cloud_)   # the source uploads while the target is indexed
         self._engine.set_clouds(self.target_cloud_, self.source_cloud_)
         self._inputs_set = True
+        self._input_source_ = self.source_cloud_   # what gicp_.setInputSource holds from here on (reference :89)
         res = self._engine.align(raise_on_failure=False)
         self.last_result = res
         log.info("GICP time: %f s", res["ms_total"] * 1e-3)
@@ -182,8 +185,10 @@ class GICPAlignment:
         self.backup_cloud_ = _copy(self.aligned_cloud_) if self.aligned_cloud_ is not None else None
         log.info("Computing iteration...")
         if not self._inputs_set:
-            self._engine.set_clouds(self.target_cloud_, self.source_cloud_)
-            self._inputs_set = True
+            # gicp_.align() without setInputSource / setInputTarget: PCL's initCompute fails, nothing converges
+            log.error("GICP no converge")
+            self._converged = False
+            return
         res = self._engine.align(raise_on_failure=False)
         self.last_result = res
         self._converged = bool(res["converged"])
@@ -194,7 +199,8 @@ class GICPAlignment:
             log.info("Converged in %f FitnessScore", self._fitness)
         else:
             log.error("GICP no converge")
-        self.aligned_cloud_ = self._engine.transform_cloud(res["transform"], self.source_cloud_)
+        # PCL's align() writes final_transformation * (the source given to setInputSource) into the cloud it is handed
+        self.aligned_cloud_ = self._engine.transform_cloud(res["transform"], self._input_source_)
 
 
 def remove_from_cloud(input_cloud, subtract_cloud, threshold, engine=None, device=0):

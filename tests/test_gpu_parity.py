@@ -495,6 +495,56 @@ def test_reference_testRunWithCov(cube_pair):
     assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)  # fine_tf_ is NOT rolled back, as upstream
 
 
+def test_zero_gate_finds_no_pairs(engine, oracle, cube_pair):
+    """setMaxCorrespondenceDistance(int) truncates (include/GICPAlignment.h:138): 0.5 becomes 0.  PCL then tests
+    `nn_dists[0] < 0`, finds no pair, throws NotEnoughPointsException inside align() and hasConverged() stays false
+    (reference :101,108 logs "GICP no converge").  A zero gate must therefore mean "no pair", not "no gate"."""
+    from leica_point_cloud_processing_b200 import GICPAlignment
+    from leica_point_cloud_processing_b200._capi import E_NOT_ENOUGH_CORRESPONDENCES
+    from oracle.oracle import default_params
+    src, tgt, _ = cube_pair
+    ref = oracle.align(src, tgt, default_params(max_corr_distance=0.0))
+    assert ref["converged"] == 0 and ref["n_pairs_last"] == 0
+    reset(engine, max_corr_distance=0.0)
+    engine.set_clouds(tgt, src)
+    pairs, idx, d2, _ = engine.correspondences(np.eye(4, dtype=np.float32))
+    assert pairs == 0 and np.all(idx == -1)
+    res = engine.align(raise_on_failure=False)
+    assert res["rc"] == E_NOT_ENOUGH_CORRESPONDENCES and res["converged"] == 0 and res["corr_pairs_last"] == 0
+    assert np.array_equal(res["transform"], np.eye(4, dtype=np.float32))
+    # the raw NN-1 hook keeps "max_dist <= 0 -> ungated"
+    gi, gd = engine.nn1(src, max_dist=0.0)
+    oi, od = oracle.nn1(tgt, src)
+    assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+    g = GICPAlignment(tgt, src, False)
+    g.setMaxCorrespondenceDistance(0.5)
+    assert g.max_corresp_distance_ == 0.0
+    g.run()
+    assert not g.hasConverged() and not g.transform_exists_
+    assert np.array_equal(g.getFineTransform(), np.eye(4, dtype=np.float32))
+    reset(engine)
+
+
+def test_iterate_keeps_the_clouds_of_the_last_run(cube_pair):
+    """reference :111-127,166-174: setSourceCloud / setTargetCloud only swap the wrapper's pointers; gicp_ keeps the
+    clouds of the last setInputSource / setInputTarget, so iterate() re-solves the OLD pair."""
+    from leica_point_cloud_processing_b200 import GICPAlignment
+    src, tgt, _ = cube_pair
+    g = GICPAlignment(tgt, src, False)
+    g.setMaxCorrespondenceDistance(5)
+    g.setTfEpsilon(5e-4)
+    g.run()
+    T1 = g.getFineTransform()
+    other = (src + np.float32(0.25)).astype(np.float32)
+    g.setSourceCloud(other)
+    g.iterate()
+    assert g.hasConverged()
+    assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)   # the same solve as run(), not one on `other`
+    fresh = GICPAlignment(tgt, src, False)
+    fresh.iterate()                                                # align() before any input was set
+    assert not fresh.hasConverged() and not fresh.transform_exists_
+
+
 # ---- the use_covariances branch: resolution, radius-normal validity, in-place point removal --------------------
 def test_cloud_resolution_matches_oracle(engine, oracle, cube_pair):
     """Utils::computeCloudResolution (reference src/Utils.cpp:145-174); the reference's test/test_utils.cpp:78-92 pins
