@@ -60,6 +60,63 @@ def test_tree_search_equals_brute_force(oracle, seed):
     assert (kd1[:, 0] == 0).all()               # the point itself (or an identical earlier point) is neighbour 0
 
 
+def _panel(n, seed=3):
+    from leica_point_cloud_processing_b200 import synth
+    return synth.panel_points(n, seed, noise_sigma=5e-4)
+
+
+@pytest.mark.parametrize("which", ["cube", "panel"])
+def test_searches_agree_with_scipy_ckdtree(oracle, cube_pair, which):
+    """Independent code (scipy.spatial.cKDTree, double arithmetic) finds the same NN-1 / kNN-20 index sets as the
+    oracle's float FLANN restatement; they may differ only where two candidates are closer to each other in distance
+    than float32 rounding can tell apart (then the oracle's answer must be one of the tied candidates)."""
+    from scipy.spatial import cKDTree
+    src, tgt, _ = cube_pair
+    cloud, qry = (tgt, src) if which == "cube" else (_panel(20000), _panel(5000, seed=4) + np.float32(0.003))
+    tree = cKDTree(cloud.astype(np.float64))
+    # NN-1
+    oi, od = oracle.nn1(cloud, qry)
+    cd, ci = tree.query(qry.astype(np.float64), k=2)
+    same = oi == ci[:, 0]
+    assert same.mean() > 0.995
+    d_exact = ((qry[~same].astype(np.float64) - cloud[oi[~same]].astype(np.float64)) ** 2).sum(1)
+    assert np.allclose(d_exact, cd[~same, 0] ** 2, rtol=2e-6, atol=1e-12)
+    assert np.allclose(od.astype(np.float64), cd[:, 0] ** 2, rtol=2e-6, atol=1e-12)
+    # kNN-20 of the cloud in itself (neighbour 0 = the point): compare index SETS
+    ki, kd = oracle.knn(cloud, 20)
+    cd, ci = tree.query(cloud.astype(np.float64), k=21)
+    bad = 0
+    for i in range(len(cloud)):
+        a, b = set(ki[i].tolist()), set(ci[i, :20].tolist())
+        if a == b:
+            continue
+        bad += 1
+        # every differing member is a tie at the 20th distance within float rounding
+        for j in a ^ b:
+            dj = ((cloud[i].astype(np.float64) - cloud[j].astype(np.float64)) ** 2).sum()
+            assert abs(dj - cd[i, 19] ** 2) <= 4e-6 * max(cd[i, 19] ** 2, 1e-12), (i, j)
+    assert bad <= 0.005 * len(cloud)
+    assert np.allclose(np.sort(kd.astype(np.float64), axis=1), cd[:, :20] ** 2, rtol=4e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("which", ["cube", "panel"])
+def test_covariances_agree_with_numpy_svd(oracle, cube_pair, which):
+    """The regularised covariance rebuilt with numpy (float32 products summed in float64 in neighbour order, LAPACK
+    SVD, singular values replaced by 1, 1, eps) equals the oracle's for EVERY point, within the bound the conditioning
+    of the smallest singular direction allows (tests/_cov_util.py normal_error_bound): no outlier allowance."""
+    from _cov_util import normal_error_bound, raw_covariances, regularised_from_svd
+    cloud = cube_pair[0] if which == "cube" else _panel(20000)
+    ki, _ = oracle.knn(cloud, 20)
+    raw = raw_covariances(cloud, ki)
+    ref, s = regularised_from_svd(raw, 1e-3)
+    cov = oracle.covariances(cloud)
+    err = np.abs(cov - ref).max(axis=(1, 2))
+    assert (err <= normal_error_bound(s)).all(), float((err / normal_error_bound(s)).max())
+    # and the bound is tight where it matters: the well-conditioned majority agrees to 1e-10
+    well = (s[:, 1] - s[:, 2]) > 1e-3 * s[:, 0]
+    assert well.mean() > 0.5 and err[well].max() < 1e-10
+
+
 def test_covariances_are_plane_to_plane(oracle, cube_pair):
     src, _, _ = cube_pair
     cov = oracle.covariances(src)
