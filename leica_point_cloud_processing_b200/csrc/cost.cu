@@ -60,6 +60,24 @@ __device__ __forceinline__ void load_pair_smem(const unsigned char* stage, int i
   }
 }
 
+// the same with explicit row bases (q rows, p rows, M rows), for stages and resident blocks of any capacity
+template <typename MT>
+__device__ __forceinline__ void load_pair_smem_at(const unsigned char* qrows, const unsigned char* prows,
+                                                  const unsigned char* mrows, int i, PairData<MT>& d) {
+  d.q = *reinterpret_cast<const float4*>(qrows + i * 16);
+  d.p = *reinterpret_cast<const float4*>(prows + i * 16);
+  const unsigned char* m = mrows + i * (6 * (int)sizeof(MT));
+  if (sizeof(MT) == 8) {
+    const double2* m2 = reinterpret_cast<const double2*>(m);
+    const double2 a = m2[0], b = m2[1], c = m2[2];
+    d.m[0] = (MT)a.x; d.m[1] = (MT)a.y; d.m[2] = (MT)b.x; d.m[3] = (MT)b.y; d.m[4] = (MT)c.x; d.m[5] = (MT)c.y;
+  } else {
+    const float2* m2 = reinterpret_cast<const float2*>(m);
+    const float2 a = m2[0], b = m2[1], c = m2[2];
+    d.m[0] = (MT)a.x; d.m[1] = (MT)a.y; d.m[2] = (MT)b.x; d.m[3] = (MT)b.y; d.m[4] = (MT)c.x; d.m[5] = (MT)c.y;
+  }
+}
+
 template <typename MT>
 __device__ __forceinline__ void add_pair(const PairData<MT>& d, const Rigid& T, double (&acc)[kCostSums]) {
   if (d.q.w == 0.f) return;  // no correspondence inside the gate
@@ -103,6 +121,112 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "r"(parity)
       : "memory");
 }
+
+// ---- block / grid reduction of the 14 sums and their publication (shared by the per-launch and the persistent kernel) ----
+// Warp shuffles -> shared-memory block tree -> per-block row of `partials` -> the last block to arrive (ticket) adds the
+// rows in a fixed order (a given input always produces the same bits) and writes `out`.  stamp != 0: `out` is mapped host
+// memory the host polls; out[15] = stamp is stored after the 14 sums are visible system-wide.  kPeer: the sums are first
+// exchanged with the other ranks through peer memory (kernels.hpp PeerReduce).  Must be called by every thread of the block.
+template <int kThreads, bool kPeer>
+__device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums], double* __restrict__ partials,
+                                                   unsigned* __restrict__ ticket, double* __restrict__ out,
+                                                   const PeerReduce& pr, unsigned stamp) {
+  constexpr int kWarps = kThreads / 32;
+  __shared__ double sm[kWarps][kCostSums + 2];
+  __shared__ double red[kThreads / 16][16];
+  __shared__ bool is_last;
+  __shared__ int timed_out;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < kCostSums; ++c) {
+    const double v = warp_sum(acc[c]);
+    if (lane == 0) sm[warp][c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kCostSums) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += sm[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(ticket, 1u);
+    is_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last block: column c = thread & 15, row group = thread >> 4; every thread sums its rows of the per-block partials
+  // (rows are 16 doubles apart: one 128-byte line per row), then the groups are added in a fixed order
+  const int c = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  double v = 0.0;
+  if (c < kCostSums)
+    for (int b = grp; b < (int)gridDim.x; b += kThreads / 16) v += __ldcg(&partials[(size_t)b * 16 + c]);
+  red[grp][c] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (threadIdx.x < kCostSums) {
+#pragma unroll
+    for (int gi = 0; gi < kThreads / 16; ++gi) s += red[gi][threadIdx.x];
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+  if (!kPeer) {
+    if (threadIdx.x < kCostSums) out[threadIdx.x] = s;
+    if (stamp) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
+    }
+    return;
+  }
+  // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
+  const int set = (int)(pr.seq & 1u);
+  if (threadIdx.x < kCostSums)
+    for (int p = 0; p < pr.world; ++p) {
+      volatile double* dst = &pr.peers[p]->vals[set][pr.rank][threadIdx.x];
+      *dst = s;
+    }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pr.world) {
+    volatile unsigned* f = &pr.peers[threadIdx.x]->flag[set][pr.rank];
+    *f = pr.seq;  // thread p tells rank p that this rank's sums of evaluation `seq` are in place
+  }
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < pr.world) {
+    volatile unsigned* f = &pr.peers[pr.rank]->flag[set][threadIdx.x];
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned spins = 0;
+    while (*f != pr.seq) {
+      if ((++spins & 0xffu) != 0u) continue;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > pr.timeout_ns) {  // wall-clock nanoseconds (not SM cycles): a peer never launched this evaluation
+        timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x < kCostSums) {
+    double t = 0.0;
+    for (int r = 0; r < pr.world; ++r) {
+      volatile double* pv = &pr.peers[pr.rank]->vals[set][r][threadIdx.x];
+      t += *pv;
+    }
+    out[threadIdx.x] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
+  }
+  if (stamp) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
+  }
+}
+
 
 // Tiles of 256 consecutive pairs are three contiguous spans in global memory (pair_tgt, src, maha).  One elected thread
 // streams them into a two-stage shared-memory ring with cp.async.bulk (TMA): the loads of the next tile are in flight
@@ -168,104 +292,162 @@ __global__ void __launch_bounds__(kCostThreads) cost_kernel(const float4* __rest
     }
   }
 
-  __shared__ double sm[kCostWarps][kCostSums + 2];
-  __shared__ double red[kCostThreads / 16][16];
-  __shared__ bool is_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < kCostSums; ++c) {
-    const double v = warp_sum(acc[c]);
-    if (lane == 0) sm[warp][c] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kCostSums) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kCostWarps; ++w) v += sm[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * 16 + threadIdx.x] = v;
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(ticket, 1u);
-    is_last = (done == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // last block: column c = thread & 15, row group = thread >> 4 (16 groups); every thread sums its rows of the
-  // per-block partials (rows are 16 doubles apart: one 128-byte line per row), then the groups are added in a
-  // fixed order - a given input always produces the same bits
-  const int c = threadIdx.x & 15, grp = threadIdx.x >> 4;
-  double v = 0.0;
-  if (c < kCostSums)
-    for (int b = grp; b < (int)gridDim.x; b += kCostThreads / 16) v += __ldcg(&partials[(size_t)b * 16 + c]);
-  red[grp][c] = v;
-  __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x < kCostSums) {
-#pragma unroll
-    for (int gi = 0; gi < kCostThreads / 16; ++gi) s += red[gi][threadIdx.x];
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
-  // stamp != 0: `out` is mapped host memory the host polls; out[15] = stamp is stored after the 14 sums are visible
-  // system-wide, so the host needs no stream synchronisation to pick the result up
-  if (!kPeer) {
-    if (threadIdx.x < kCostSums) out[threadIdx.x] = s;
-    if (stamp) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
-    }
-    return;
-  }
-  // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
-  const int set = (int)(pr.seq & 1u);
-  if (threadIdx.x < kCostSums)
-    for (int p = 0; p < pr.world; ++p) {
-      volatile double* dst = &pr.peers[p]->vals[set][pr.rank][threadIdx.x];
-      *dst = s;
-    }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < pr.world) {
-    volatile unsigned* f = &pr.peers[threadIdx.x]->flag[set][pr.rank];
-    *f = pr.seq;  // thread p tells rank p that this rank's sums of evaluation `seq` are in place
-  }
-  __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
-  __syncthreads();
-  if (threadIdx.x < pr.world) {
-    volatile unsigned* f = &pr.peers[pr.rank]->flag[set][threadIdx.x];
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    unsigned spins = 0;
-    while (*f != pr.seq) {
-      if ((++spins & 0xffu) != 0u) continue;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > pr.timeout_ns) {  // wall-clock nanoseconds (not SM cycles): a peer never launched this evaluation
-        timed_out = 1;
-        break;
-      }
-    }
-  }
-  __syncthreads();
-  __threadfence_system();
-  if (threadIdx.x < kCostSums) {
-    double t = 0.0;
-    for (int r = 0; r < pr.world; ++r) {
-      volatile double* v = &pr.peers[pr.rank]->vals[set][r][threadIdx.x];
-      t += *v;
-    }
-    out[threadIdx.x] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
-  }
-  if (stamp) {
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
-  }
+  reduce_and_publish<kCostThreads, kPeer>(acc, partials, ticket, out, pr, stamp);
 }
 
+// ---- persistent evaluation kernel: one launch per OUTER iteration, one command per evaluation ------------------------------
+// The BFGS line search evaluates the same pairs 20-30 times per outer iteration with a different transform each time,
+// and the host needs every result before it can choose the next transform: per evaluation the per-launch kernel pays a
+// launch, the ramp of 296 blocks, 80 B per pair from L2 and a tail.  This kernel is launched once when the pairs of an
+// outer iteration exist and stays resident, one block per SM:
+//   * every block owns a fixed contiguous range of pairs; the first `resident` of them are copied into its shared
+//     memory ONCE (one cp.async.bulk per span) and never leave it: at 1 M pairs that is 30 % of the pairs (all of them
+//     up to 0.3 M pairs) that cost no L2 traffic in any evaluation; the rest streams through a ring of kStages tiles as
+//     in cost_kernel, cyclically, so the first tiles of the NEXT evaluation are already in flight while the host thinks;
+//   * a command (transform, stamp) arrives in mapped host memory; block 0 polls it and republishes it in device memory,
+//     where the other blocks poll (one PCIe reader, not 148); the result goes back through the polled stamp as before;
+//   * block 0 ends the kernel on an EXIT command, or by itself when no command arrived for idle_timeout_ns (a host that
+//     threw an exception, was descheduled, or died): the host notices that the stream has drained and launches again.
+// Sums, order of operations and therefore bits are those of cost_kernel with the same grid.
+template <typename MT, bool kPeer, int kThreads, int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+cost_persistent_kernel(const float4* __restrict__ src, int lo, int n, const float4* __restrict__ pair_tgt,
+                       const MT* __restrict__ maha, const CostCommand* hcmd, CostCommand* dcmd, unsigned epoch,
+                       double* __restrict__ partials, unsigned* __restrict__ ticket, double* __restrict__ out, PeerReduce pr,
+                       unsigned long long idle_timeout_ns, int resident_cap) {
+  constexpr int kRowM = 6 * (int)sizeof(MT);
+  constexpr int kRow = 32 + kRowM;
+  constexpr int kStageBytes = kThreads * kRow;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ __align__(8) unsigned long long full[kStages];
+  __shared__ __align__(8) unsigned long long res_bar;
+  __shared__ CostCommand s_cmd;
+  unsigned char* ring = dyn;                                  // kStages stages of kThreads pairs
+  unsigned char* res = dyn + (size_t)kStages * kStageBytes;   // resident pairs: q rows, p rows, M rows
+
+  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int b0 = min(n, (int)blockIdx.x * per);
+  const int cnt = min(n - b0, per);
+  const int r = min(cnt, resident_cap);
+  const int streamed = cnt - r;
+  const int ntiles = (streamed + kThreads - 1) / kThreads;
+  auto tile_pairs = [&](int t) { return min(kThreads, streamed - t * kThreads); };
+  auto issue = [&](unsigned k) {  // cyclic tile k into stage k % kStages (thread 0 only)
+    const int t = (int)(k % (unsigned)ntiles), st = (int)(k % (unsigned)kStages);
+    const int np = tile_pairs(t);
+    const size_t t0 = (size_t)b0 + r + (size_t)t * kThreads;
+    unsigned char* stage = ring + st * kStageBytes;
+    mbar_expect_tx(&full[st], (unsigned)(np * kRow));
+    bulk_g2s(stage, pair_tgt + t0, np * 16, &full[st]);
+    bulk_g2s(stage + kThreads * 16, src + lo + t0, np * 16, &full[st]);
+    bulk_g2s(stage + kThreads * 32, maha + 6 * t0, np * kRowM, &full[st]);
+  };
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) mbar_init(&full[st], 1);
+    mbar_init(&res_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (r > 0) {
+      mbar_expect_tx(&res_bar, (unsigned)(r * kRow));
+      bulk_g2s(res, pair_tgt + b0, r * 16, &res_bar);
+      bulk_g2s(res + (size_t)resident_cap * 16, src + lo + b0, r * 16, &res_bar);
+      bulk_g2s(res + (size_t)resident_cap * 32, maha + 6 * (size_t)b0, r * kRowM, &res_bar);
+    }
+    if (ntiles > 0)
+      for (unsigned k = 0; k < (unsigned)kStages; ++k) issue(k);
+  }
+  if (r > 0) mbar_wait(&res_bar, 0u);
+
+  unsigned consumed = 0;  // tiles consumed so far (all evaluations)
+  unsigned count = 0;     // commands seen by this launch
+  for (;;) {
+    // ---- next command -------------------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+      const unsigned want = (epoch << 20) | ((count + 1u) & 0xfffffu);
+      if (blockIdx.x == 0) {
+        const volatile unsigned* hseq = &hcmd->seq;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        bool dead = false;
+        for (unsigned spins = 1; *hseq != want; ++spins) {
+          if ((spins & 0x3fu) != 0u) continue;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > idle_timeout_ns) { dead = true; break; }
+        }
+        __threadfence_system();
+        if (dead) {
+          s_cmd.op = kCostOpExit;
+        } else {
+          const volatile CostCommand* h = hcmd;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) s_cmd.T[i] = h->T[i];
+          s_cmd.op = h->op;
+          s_cmd.stamp = h->stamp;
+          s_cmd.peer_seq = h->peer_seq;
+        }
+        volatile CostCommand* d = dcmd;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) d->T[i] = s_cmd.T[i];
+        d->op = s_cmd.op;
+        d->stamp = s_cmd.stamp;
+        d->peer_seq = s_cmd.peer_seq;
+        __threadfence();
+        d->seq = want;
+      } else {
+        const volatile CostCommand* d = dcmd;
+        while (d->seq != want) {
+        }
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) s_cmd.T[i] = d->T[i];
+        s_cmd.op = d->op;
+        s_cmd.stamp = d->stamp;
+        s_cmd.peer_seq = d->peer_seq;
+      }
+    }
+    __syncthreads();
+    ++count;
+    if (s_cmd.op != kCostOpEval) break;
+    Rigid T;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) T.m[i] = s_cmd.T[i];
+    const unsigned stamp = s_cmd.stamp;
+    PeerReduce prr = pr;
+    prr.seq = s_cmd.peer_seq;
+
+    double acc[kCostSums];
+#pragma unroll
+    for (int c = 0; c < kCostSums; ++c) acc[c] = 0.0;
+    // resident pairs: no memory traffic beyond shared memory
+    for (int i = threadIdx.x; i < r; i += kThreads) {
+      PairData<MT> d;
+      load_pair_smem_at<MT>(res, res + (size_t)resident_cap * 16, res + (size_t)resident_cap * 32, i, d);
+      add_pair(d, T, acc);
+    }
+    // streamed pairs
+    for (int t = 0; t < ntiles; ++t, ++consumed) {
+      const int st = (int)(consumed % (unsigned)kStages);
+      mbar_wait(&full[st], (consumed / (unsigned)kStages) & 1u);
+      if ((int)threadIdx.x < tile_pairs((int)(consumed % (unsigned)ntiles))) {
+        const unsigned char* stage = ring + st * kStageBytes;
+        PairData<MT> d;
+        load_pair_smem_at<MT>(stage, stage + kThreads * 16, stage + kThreads * 32, threadIdx.x, d);
+        add_pair(d, T, acc);
+      }
+      __syncthreads();  // every thread has read stage st: it may be refilled (with a tile of this or the next evaluation)
+      if (threadIdx.x == 0) issue(consumed + (unsigned)kStages);
+    }
+    reduce_and_publish<kThreads, kPeer>(acc, partials, ticket, out, prr, stamp);
+    __syncthreads();
+  }
+  // leave no bulk copy in flight into this block's shared memory
+  if (ntiles > 0)
+    for (unsigned k = consumed; k < consumed + (unsigned)kStages; ++k)
+      mbar_wait(&full[k % (unsigned)kStages], (k / (unsigned)kStages) & 1u);
+}
 
 // ---- second-order moments of the objective (one pass per OUTER iteration) ---------------------------------------------
 // The objective is a quadratic form in the 12 entries of the rigid transform: with r0_i the residual at the transform
@@ -400,6 +582,58 @@ void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const
                                                                       ticket, out14, pr, stamp);
   }
   GICPB_LAUNCHED();
+}
+
+// ---- persistent session ---------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kPersThreads = 512;  // one block per SM
+constexpr int kPersStages = 2;     // 2 x 512 pairs x 80 B = 80 KB in flight per SM
+
+template <typename MT, bool kPeer>
+void launch_persistent_t(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, const CostCommand* hcmd,
+                         CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket, double* out,
+                         const PeerReduce& pr, unsigned long long idle_ns, int blocks, int smem_optin, cudaStream_t stream) {
+  constexpr int kRow = 32 + 6 * (int)sizeof(MT);
+  auto kern = cost_persistent_kernel<MT, kPeer, kPersThreads, kPersStages>;
+  cudaFuncAttributes fa;
+  GICPB_CUDA(cudaFuncGetAttributes(&fa, kern));
+  const int ring = kPersStages * kPersThreads * kRow;
+  const int budget = smem_optin - (int)fa.sharedSizeBytes - ring - 1024;  // 1 KB of slack for alignment
+  const int per = (n + blocks - 1) / blocks;
+  int resident = std::max(0, std::min(per, budget / kRow));
+  resident &= ~15;  // row bases stay 16-byte (M rows: 128-byte) aligned
+  if (resident == 0 && per > 0 && budget >= 16 * kRow) resident = std::min(16, per) & ~15;
+  const size_t dyn = (size_t)ring + (size_t)resident * kRow;
+  GICPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  kern<<<blocks, kPersThreads, dyn, stream>>>(src, lo, n, pair_tgt, (const MT*)maha, hcmd, dcmd, epoch, partials, ticket, out,
+                                              pr, idle_ns, resident);
+  GICPB_LAUNCHED();
+}
+}  // namespace
+
+int cost_persistent_blocks(int num_sms) { return num_sms; }
+
+void launch_cost_persistent(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
+                            const CostCommand* hcmd_dev, CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket,
+                            double* out16, const PeerReduce* peer, unsigned long long idle_timeout_ns, int blocks,
+                            int smem_optin, cudaStream_t stream) {
+  PeerReduce pr{};
+  if (peer) pr = *peer;
+  if (maha_fp32) {
+    if (peer)
+      launch_persistent_t<float, true>(src, lo, n, pair_tgt, maha, hcmd_dev, dcmd, epoch, partials, ticket, out16, pr,
+                                       idle_timeout_ns, blocks, smem_optin, stream);
+    else
+      launch_persistent_t<float, false>(src, lo, n, pair_tgt, maha, hcmd_dev, dcmd, epoch, partials, ticket, out16, pr,
+                                        idle_timeout_ns, blocks, smem_optin, stream);
+  } else {
+    if (peer)
+      launch_persistent_t<double, true>(src, lo, n, pair_tgt, maha, hcmd_dev, dcmd, epoch, partials, ticket, out16, pr,
+                                        idle_timeout_ns, blocks, smem_optin, stream);
+    else
+      launch_persistent_t<double, false>(src, lo, n, pair_tgt, maha, hcmd_dev, dcmd, epoch, partials, ticket, out16, pr,
+                                         idle_timeout_ns, blocks, smem_optin, stream);
+  }
 }
 
 int moments_grid_blocks(int n, int num_sms) {

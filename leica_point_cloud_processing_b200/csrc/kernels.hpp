@@ -139,6 +139,25 @@ void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const
 // stamp != 0: out14 must be mapped host memory of 16 doubles; the kernel stores (double)stamp into out14[15] once the 14
 // sums are visible to the host, which can then poll that word instead of synchronising the stream.
 
+// Persistent evaluation kernel (cost.cu cost_persistent_kernel): launched once per outer iteration, one block per SM; every
+// evaluation is a CostCommand the host writes into mapped pinned memory (seq LAST) and the kernel answers through the
+// stamp in out16[15].  seq = (epoch << 20) | k for the k-th command (k = 1, 2, ...) of the launch with that epoch.
+constexpr unsigned kCostOpEval = 1u, kCostOpExit = 2u;
+struct CostCommand {
+  float T[12];        // upper three rows of the float transform, row-major
+  unsigned op;        // kCostOpEval / kCostOpExit
+  unsigned stamp;     // stored (as a double) into out16[15] when the 14 sums are visible to the host
+  unsigned peer_seq;  // PeerReduce::seq of this evaluation (fused cross-GPU sum)
+  unsigned seq;       // written last by the host; polled by block 0
+};
+int cost_persistent_blocks(int num_sms);
+// hcmd_dev: device alias of the mapped host command; dcmd: one CostCommand in device memory; partials / ticket as
+// launch_cost (blocks rows); out16: mapped host memory of 16 doubles; smem_optin: cudaDevAttrMaxSharedMemoryPerBlockOptin.
+void launch_cost_persistent(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
+                            const CostCommand* hcmd_dev, CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket,
+                            double* out16, const PeerReduce* peer, unsigned long long idle_timeout_ns, int blocks,
+                            int smem_optin, cudaStream_t stream);
+
 // ---- segment.cu -----------------------------------------------------------------------------------------
 // Euclidean clustering: joins every pair of indexed points of `g` with d2 < r2 (strict) in a union-find over sorted
 // positions (`parent`, g.n ints) and writes root_of[original index] = original index of the set's root point
