@@ -68,6 +68,9 @@ typedef struct gicpb_params {
                                    * one all-reduce per outer iteration instead of one per evaluation).  Same
                                    * objective with exact T*p: values agree to ~1e-8 relative, which PCL's line
                                    * search amplifies to ~2e-4 in the final transform */
+  int cost_persistent;            /* 1 (default): the evaluations of one inner solve are commands to ONE resident kernel
+                                   * (launched per outer iteration, a third of the pairs parked in shared memory) instead of
+                                   * one launch each; same sums, same bits.  0: one launch per evaluation */
 } gicpb_params;
 
 typedef struct gicpb_align_result {

@@ -37,6 +37,7 @@ class Params(ctypes.Structure):
         ("use_previous_match", ctypes.c_int),
         ("l2_persist", ctypes.c_int),
         ("cost_moments", ctypes.c_int),
+        ("cost_persistent", ctypes.c_int),
     ]
 
 

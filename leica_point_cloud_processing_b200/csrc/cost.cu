@@ -9,6 +9,9 @@
 // computeRDerivative.  FP32 transform + FP64 accumulate: no dense contraction, tensor cores do not apply.
 //
 // Algorithmic bytes per pair: 16 (p_src float4) + 16 (p_tgt float4) + 48 (M, 6 doubles) or 24 (6 floats).
+#include <algorithm>
+#include <cstdlib>
+
 #include "kernels.hpp"
 
 namespace gicpb {
@@ -113,6 +116,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
@@ -321,11 +332,12 @@ cost_persistent_kernel(const float4* __restrict__ src, int lo, int n, const floa
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ __align__(8) unsigned long long full[kStages];
   __shared__ __align__(8) unsigned long long res_bar;
-  __shared__ CostCommand s_cmd;
+  __shared__ struct { float T[12]; unsigned op, stamp, peer_seq; } s_cmd;
   unsigned char* ring = dyn;                                  // kStages stages of kThreads pairs
   unsigned char* res = dyn + (size_t)kStages * kStageBytes;   // resident pairs: q rows, p rows, M rows
 
-  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  // pairs per block: a multiple of 16, so that every bulk copy starts on a 16-byte boundary whatever the row width
+  const int per = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 15) & ~15;
   const int b0 = min(n, (int)blockIdx.x * per);
   const int cnt = min(n - b0, per);
   const int r = min(cnt, resident_cap);
@@ -337,10 +349,13 @@ cost_persistent_kernel(const float4* __restrict__ src, int lo, int n, const floa
     const int np = tile_pairs(t);
     const size_t t0 = (size_t)b0 + r + (size_t)t * kThreads;
     unsigned char* stage = ring + st * kStageBytes;
-    mbar_expect_tx(&full[st], (unsigned)(np * kRow));
+    // bulk copies move multiples of 16 bytes: an odd number of 24-byte float rows is rounded up (the 8 extra bytes are
+    // the next pair's, or lie inside the allocation, which is sized for 48-byte rows)
+    const int mbytes = (np * kRowM + 15) & ~15;
+    mbar_expect_tx(&full[st], (unsigned)(np * 32 + mbytes));
     bulk_g2s(stage, pair_tgt + t0, np * 16, &full[st]);
     bulk_g2s(stage + kThreads * 16, src + lo + t0, np * 16, &full[st]);
-    bulk_g2s(stage + kThreads * 32, maha + 6 * t0, np * kRowM, &full[st]);
+    bulk_g2s(stage + kThreads * 32, maha + 6 * t0, mbytes, &full[st]);
   };
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -351,10 +366,11 @@ cost_persistent_kernel(const float4* __restrict__ src, int lo, int n, const floa
   __syncthreads();
   if (threadIdx.x == 0) {
     if (r > 0) {
-      mbar_expect_tx(&res_bar, (unsigned)(r * kRow));
+      const int mbytes = (r * kRowM + 15) & ~15;
+      mbar_expect_tx(&res_bar, (unsigned)(r * 32 + mbytes));
       bulk_g2s(res, pair_tgt + b0, r * 16, &res_bar);
       bulk_g2s(res + (size_t)resident_cap * 16, src + lo + b0, r * 16, &res_bar);
-      bulk_g2s(res + (size_t)resident_cap * 32, maha + 6 * (size_t)b0, r * kRowM, &res_bar);
+      bulk_g2s(res + (size_t)resident_cap * 32, maha + 6 * (size_t)b0, mbytes, &res_bar);
     }
     if (ntiles > 0)
       for (unsigned k = 0; k < (unsigned)kStages; ++k) issue(k);
@@ -365,47 +381,45 @@ cost_persistent_kernel(const float4* __restrict__ src, int lo, int n, const floa
   unsigned count = 0;     // commands seen by this launch
   for (;;) {
     // ---- next command -------------------------------------------------------------------------------------------
-    if (threadIdx.x == 0) {
+    // lanes 0-4 of warp 0 each own one 16-byte chunk of the command (kernels.hpp CostCommand)
+    if (threadIdx.x < 32) {
       const unsigned want = (epoch << 20) | ((count + 1u) & 0xfffffu);
+      const int lane = threadIdx.x;
+      uint4 v = make_uint4(0u, 0u, 0u, want);
       if (blockIdx.x == 0) {
-        const volatile unsigned* hseq = &hcmd->seq;
-        unsigned long long t0, t1;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned long long t0 = 0, t1;
+        if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         bool dead = false;
-        for (unsigned spins = 1; *hseq != want; ++spins) {
-          if ((spins & 0x3fu) != 0u) continue;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-          if (t1 - t0 > idle_timeout_ns) { dead = true; break; }
+        for (unsigned spins = 1;; ++spins) {
+          if (lane < 5) v = ld_volatile_v4(reinterpret_cast<const uint4*>(&hcmd->chunk[lane]));
+          if (__all_sync(kFullMask, lane >= 5 || v.w == want)) break;
+          if ((spins & 0x1fu) == 0u) {
+            int d = 0;
+            if (lane == 0) {
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              d = (t1 - t0 > idle_timeout_ns) ? 1 : 0;
+            }
+            if (__shfl_sync(kFullMask, d, 0)) { dead = true; break; }
+          }
         }
-        __threadfence_system();
-        if (dead) {
-          s_cmd.op = kCostOpExit;
-        } else {
-          const volatile CostCommand* h = hcmd;
-#pragma unroll
-          for (int i = 0; i < 12; ++i) s_cmd.T[i] = h->T[i];
-          s_cmd.op = h->op;
-          s_cmd.stamp = h->stamp;
-          s_cmd.peer_seq = h->peer_seq;
-        }
-        volatile CostCommand* d = dcmd;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) d->T[i] = s_cmd.T[i];
-        d->op = s_cmd.op;
-        d->stamp = s_cmd.stamp;
-        d->peer_seq = s_cmd.peer_seq;
-        __threadfence();
-        d->seq = want;
+        if (dead) v = make_uint4(kCostOpExit, 0u, 0u, want);  // only chunk 4's first word matters
+        if (dead && lane != 4) v = make_uint4(0u, 0u, 0u, want);
+        // republish for the other blocks: payload and sequence word of a chunk travel in one 16-byte store
+        if (lane < 5) st_volatile_v4(reinterpret_cast<uint4*>(&dcmd->chunk[lane]), v);
       } else {
-        const volatile CostCommand* d = dcmd;
-        while (d->seq != want) {
+        for (;;) {
+          if (lane < 5) v = ld_volatile_v4(reinterpret_cast<const uint4*>(&dcmd->chunk[lane]));
+          if (__all_sync(kFullMask, lane >= 5 || v.w == want)) break;
         }
-        __threadfence();
-#pragma unroll
-        for (int i = 0; i < 12; ++i) s_cmd.T[i] = d->T[i];
-        s_cmd.op = d->op;
-        s_cmd.stamp = d->stamp;
-        s_cmd.peer_seq = d->peer_seq;
+      }
+      if (lane < 4) {
+        s_cmd.T[3 * lane] = __uint_as_float(v.x);
+        s_cmd.T[3 * lane + 1] = __uint_as_float(v.y);
+        s_cmd.T[3 * lane + 2] = __uint_as_float(v.z);
+      } else if (lane == 4) {
+        s_cmd.op = v.x;
+        s_cmd.stamp = v.y;
+        s_cmd.peer_seq = v.z;
       }
     }
     __syncthreads();
@@ -586,28 +600,59 @@ void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const
 
 // ---- persistent session ---------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kPersThreads = 512;  // one block per SM
-constexpr int kPersStages = 2;     // 2 x 512 pairs x 80 B = 80 KB in flight per SM
+template <typename MT, bool kPeer, int kThreads, int kStages>
+void launch_persistent_v(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, const CostCommand* hcmd,
+                         CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket, double* out,
+                         const PeerReduce& pr, unsigned long long idle_ns, int blocks, int smem_optin, cudaStream_t stream) {
+  constexpr int kRow = 32 + 6 * (int)sizeof(MT);
+  auto kern = cost_persistent_kernel<MT, kPeer, kThreads, kStages>;
+  static int static_smem = -1;  // of this instantiation
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    GICPB_CUDA(cudaFuncGetAttributes(&fa, kern));
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int ring = kStages * kThreads * kRow;
+  const int budget = smem_optin - static_smem - ring - 1024;  // 1 KB of slack for alignment
+  const int per = ((n + blocks - 1) / blocks + 15) & ~15;
+  // a multiple of 16 pairs: the row bases of the resident block stay 128-byte aligned
+  const int resident = std::max(0, std::min(per, (budget / kRow) & ~15));
+  const size_t dyn = (size_t)ring + (size_t)resident * kRow;
+  GICPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  kern<<<blocks, kThreads, dyn, stream>>>(src, lo, n, pair_tgt, (const MT*)maha, hcmd, dcmd, epoch, partials, ticket, out, pr,
+                                          idle_ns, resident);
+  GICPB_LAUNCHED();
+}
+
+// block shape of the resident kernel: 512 threads x 2 stages keeps 80 KB in flight per SM and parks 26 % of 1 M pairs;
+// GICPB_COST_VARIANT=1: 256 x 3 (60 KB, 30 %), 2: 256 x 2 (40 KB, 34 %) - kept selectable for measurements
+int persistent_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("GICPB_COST_VARIANT");
+    v = e && *e ? std::atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return v;
+}
 
 template <typename MT, bool kPeer>
 void launch_persistent_t(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, const CostCommand* hcmd,
                          CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket, double* out,
                          const PeerReduce& pr, unsigned long long idle_ns, int blocks, int smem_optin, cudaStream_t stream) {
-  constexpr int kRow = 32 + 6 * (int)sizeof(MT);
-  auto kern = cost_persistent_kernel<MT, kPeer, kPersThreads, kPersStages>;
-  cudaFuncAttributes fa;
-  GICPB_CUDA(cudaFuncGetAttributes(&fa, kern));
-  const int ring = kPersStages * kPersThreads * kRow;
-  const int budget = smem_optin - (int)fa.sharedSizeBytes - ring - 1024;  // 1 KB of slack for alignment
-  const int per = (n + blocks - 1) / blocks;
-  int resident = std::max(0, std::min(per, budget / kRow));
-  resident &= ~15;  // row bases stay 16-byte (M rows: 128-byte) aligned
-  if (resident == 0 && per > 0 && budget >= 16 * kRow) resident = std::min(16, per) & ~15;
-  const size_t dyn = (size_t)ring + (size_t)resident * kRow;
-  GICPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-  kern<<<blocks, kPersThreads, dyn, stream>>>(src, lo, n, pair_tgt, (const MT*)maha, hcmd, dcmd, epoch, partials, ticket, out,
-                                              pr, idle_ns, resident);
-  GICPB_LAUNCHED();
+  switch (persistent_variant()) {
+    case 1:
+      launch_persistent_v<MT, kPeer, 256, 3>(src, lo, n, pair_tgt, maha, hcmd, dcmd, epoch, partials, ticket, out, pr, idle_ns,
+                                             blocks, smem_optin, stream);
+      break;
+    case 2:
+      launch_persistent_v<MT, kPeer, 256, 2>(src, lo, n, pair_tgt, maha, hcmd, dcmd, epoch, partials, ticket, out, pr, idle_ns,
+                                             blocks, smem_optin, stream);
+      break;
+    default:
+      launch_persistent_v<MT, kPeer, 512, 2>(src, lo, n, pair_tgt, maha, hcmd, dcmd, epoch, partials, ticket, out, pr, idle_ns,
+                                             blocks, smem_optin, stream);
+  }
 }
 }  // namespace
 

@@ -143,15 +143,21 @@ void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const
 // evaluation is a CostCommand the host writes into mapped pinned memory (seq LAST) and the kernel answers through the
 // stamp in out16[15].  seq = (epoch << 20) | k for the k-th command (k = 1, 2, ...) of the launch with that epoch.
 constexpr unsigned kCostOpEval = 1u, kCostOpExit = 2u;
+// A command is five self-validating 16-byte chunks: each carries the sequence word in its last lane, and the host writes
+// a chunk's payload before its sequence word.  A 16-byte read (one PCIe read inside one cache line, or one L2 access)
+// that shows the expected sequence word therefore shows that command's payload: five lanes read the five chunks IN
+// PARALLEL (one round trip) instead of seventeen dependent reads.
 struct CostCommand {
-  float T[12];        // upper three rows of the float transform, row-major
-  unsigned op;        // kCostOpEval / kCostOpExit
-  unsigned stamp;     // stored (as a double) into out16[15] when the 14 sums are visible to the host
-  unsigned peer_seq;  // PeerReduce::seq of this evaluation (fused cross-GPU sum)
-  unsigned seq;       // written last by the host; polled by block 0
+  struct Chunk {
+    unsigned w[3];  // chunks 0-3: the bits of T[3i .. 3i+2]; chunk 4: op, stamp, peer_seq
+    unsigned seq;
+  } chunk[5];
+  unsigned pad[12];  // 128 bytes: two commands never share a line
 };
+static_assert(sizeof(CostCommand) == 128, "CostCommand layout");
 int cost_persistent_blocks(int num_sms);
-// hcmd_dev: device alias of the mapped host command; dcmd: one CostCommand in device memory; partials / ticket as
+// hcmd_dev: device alias of the mapped host command slot of this launch (the host alternates between two slots by epoch,
+// so the EXIT of one launch is never overwritten by the first command of the next); dcmd: one CostCommand in device memory; partials / ticket as
 // launch_cost (blocks rows); out16: mapped host memory of 16 doubles; smem_optin: cudaDevAttrMaxSharedMemoryPerBlockOptin.
 void launch_cost_persistent(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                             const CostCommand* hcmd_dev, CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket,

@@ -19,7 +19,7 @@ FIT_TOL_REL = 1e-4
 def reset(engine, **kw):
     base = dict(max_iterations=100, transformation_epsilon=4e-3, rotation_epsilon=2e-3, max_corr_distance=4e-2,
                 k_correspondences=20, gicp_epsilon=1e-3, max_inner_iterations=20, cell_size=0.0, points_per_cell=3.0,
-                mahalanobis_fp32=0, use_previous_match=1, cost_moments=0)
+                mahalanobis_fp32=0, use_previous_match=1, cost_moments=0, cost_persistent=1)
     base.update(kw)
     engine.set_params(**base)
 
@@ -242,6 +242,62 @@ def test_align_panel_100k_matches_oracle(engine, oracle):
     fit = engine.fitness(res["transform"])
     fit_ref = oracle.fitness(src, tgt, ref["T"])
     assert abs(fit - fit_ref) <= FIT_TOL_REL * fit_ref
+
+
+@pytest.mark.parametrize("n,fp32", [(5000, 0), (3001, 1), (120_000, 0), (400_001, 1), (400_001, 0)])
+def test_resident_cost_kernel_is_bit_identical(engine, n, fp32):
+    """cost_persistent=1 (one resident kernel per inner solve, commands through mapped memory, a part of the pairs parked
+    in shared memory) against cost_persistent=0 (one launch per evaluation): the same sums in the same order, so every
+    evaluation, the trajectory and the final transform are bit-identical - for pair counts below, at and above what the
+    resident blocks hold, odd counts, and both Mahalanobis widths."""
+    src, tgt, _ = synth.make_pair(n, n)
+    out = {}
+    for mode in (0, 1):
+        reset(engine, max_corr_distance=1.0, cost_persistent=mode, mahalanobis_fp32=fp32)
+        engine.set_clouds(tgt, src)
+        res = engine.align()
+        out[mode] = res
+        x = np.array([0.01, -0.02, 0.015, 0.02, -0.01, 0.03])
+        f, g = engine.cost(x)            # the single-evaluation hook (always one launch) on the final pairs
+        out[mode, "fg"] = (f, g)
+    assert out[0]["converged"] == 1
+    assert np.array_equal(out[0]["transform"], out[1]["transform"])
+    assert out[0]["cost_evaluations"] == out[1]["cost_evaluations"]
+    assert out[0]["outer_iterations"] == out[1]["outer_iterations"]
+    assert out[0, "fg"][0] == out[1, "fg"][0] and np.array_equal(out[0, "fg"][1], out[1, "fg"][1])
+    # the resident session's own evaluations against the per-launch kernel at the same x
+    T = out[1]["transform"]
+    ms_res, _ = engine.bench_kernel(4, T, iters=5)
+    ms_one, _ = engine.bench_kernel(5, T, iters=5)
+    assert ms_res > 0 and ms_one > 0
+    reset(engine)
+
+
+def test_resident_cost_kernel_survives_an_idle_host(engine):
+    """The resident kernel ends itself when no command arrives for GICPB_COST_IDLE_MS; an evaluation that finds it gone
+    launches it again.  With the host stalled longer than that before EVERY command (test knob) each evaluation takes the
+    relaunch path, and the result is still bit-identical."""
+    import os
+    from leica_point_cloud_processing_b200 import Engine
+    src, tgt, _ = synth.make_pair(50_000, 50_000)
+    reset(engine, max_corr_distance=1.0, max_iterations=2)
+    engine.set_clouds(tgt, src)
+    ref = engine.align()
+    os.environ["GICPB_COST_IDLE_MS"] = "2"
+    os.environ["GICPB_COST_TEST_STALL_MS"] = "8"
+    try:
+        e = Engine(0)
+    finally:
+        del os.environ["GICPB_COST_IDLE_MS"], os.environ["GICPB_COST_TEST_STALL_MS"]
+    e.set_params(max_corr_distance=1.0, max_iterations=2, points_per_cell=3.0)
+    e.set_clouds(tgt, src)
+    launches0 = e.launch_count()
+    r = e.align()
+    relaunched = e.launch_count() - launches0
+    e.close()
+    assert np.array_equal(r["transform"], ref["transform"]) and r["cost_evaluations"] == ref["cost_evaluations"]
+    assert relaunched >= r["cost_evaluations"]   # (nearly) one launch of the resident kernel per evaluation
+    reset(engine)
 
 
 def test_align_cost_moments_mode(engine, oracle):
