@@ -69,11 +69,8 @@ template <class Msg, class Cloud>
 inline void fromROSMsg(const Msg& msg, Cloud& cloud, Context* shared = nullptr) {
   gicpb_pc2_layout lay;
   if (!pointcloud2Layout(msg, &lay)) throw std::runtime_error("fromROSMsg: the message has no FLOAT32 x / y / z fields");
-  std::unique_ptr<Context> own;
-  if (!shared) {
-    own.reset(new Context);
-    shared = own.get();
-  }
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
   cloud.points.resize((size_t)msg.width * msg.height);
   cloud.width = msg.width;
   cloud.height = msg.height;
@@ -112,11 +109,8 @@ inline void toROSMsg(const Cloud& cloud, Msg& msg) {
 // returns 0, or -1 like pcl::io::loadPCDFile when the file cannot be read (the reason is logged)
 template <class Cloud>
 inline int loadPCDFile(const std::string& file_name, Cloud& cloud, Context* shared = nullptr) {
-  std::unique_ptr<Context> own;
-  if (!shared) {
-    own.reset(new Context);
-    shared = own.get();
-  }
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
   gicpb_pcd_info info;
   if (gicpb_pcd_load_xyzrgb(shared->get(), file_name.c_str(), nullptr, 0, 0, &info) != GICPB_OK) {
     log(kError, "[pcl::PCDReader::read] %s", gicpb_last_error(shared->get()));

@@ -37,11 +37,8 @@ template <class CloudPtr>
 inline void downsampleCloud(const CloudPtr& cloud, const CloudPtr& cloud_downsampled, double leaf_size,
                             Context* shared = nullptr) {
   log(kInfo, "Downsample cloud with leaf_size : %f", leaf_size);
-  std::unique_ptr<Context> own;
-  if (!shared) {
-    own.reset(new Context);
-    shared = own.get();
-  }
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
   CloudT out;
   const int64_t n = (int64_t)cloud->points.size();
   if (n > 0) {
@@ -71,7 +68,8 @@ class FODDetector {
   typedef gicpb_shim::PointIndicesT PointIndices;
 
   // reference src/FODDetector.cpp:21-26
-  FODDetector(CloudPtr cloud, double cluster_tolerance, double min_fod_points) : cloud_(cloud) {
+  FODDetector(CloudPtr cloud, double cluster_tolerance, double min_fod_points)
+      : ctx_holder_(gicpb_shim::Context::shared()), ctx_(*ctx_holder_), cloud_(cloud) {
     setClusterTolerance(cluster_tolerance);
     setMinFODpoints(min_fod_points);
   }
@@ -142,7 +140,8 @@ class FODDetector {
 #endif
 
  private:
-  gicpb_shim::Context ctx_;
+  std::shared_ptr<gicpb_shim::Context> ctx_holder_;  // the process-wide context (GICPAlignment_b200.hpp)
+  gicpb_shim::Context& ctx_;
   CloudPtr cloud_;
   double cluster_tolerance_;
   double min_cluster_size_;

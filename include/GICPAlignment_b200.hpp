@@ -13,6 +13,7 @@
 //   - use_covariances: the points without a finite radius-search normal are dropped from the CALLER's clouds
 //     (:63-67); the covariances themselves are reset by setInputSource/Target in PCL 1.8.1 and never reach the
 //     solver, see getCovariances() below.
+//   - setSourceCloud / setTargetCloud do not reach gicp_: iterate() keeps solving the pair of the last run()  (:111-127,166-174)
 //
 // With -DGICPB_WITH_PCL the clouds are pcl::PointCloud<pcl::PointXYZRGB>::Ptr and the matrix Eigen::Matrix4f, as
 // in the reference.  Without it (this repo's tests; PCL and Eigen are not in the image) the same code runs on the
@@ -145,7 +146,11 @@ inline bool isValidTransform(const Mat4T& tf) {
   return true;
 }
 
-// one engine context per object; device from GICPB_DEVICE (default 0)
+// One engine context (stream, pinned staging ring, device buffers) is shared by every shim object of the process by
+// default - GICPAlignment, removeFromCloud, FODDetector, downsampleCloud, getNormals, the cloud I/O helpers - as one
+// LeicaStateMachine run uses them one after the other (reference src/LeicaStateMachine.cpp:138-216): nothing is created
+// and torn down per stage.  Device from GICPB_DEVICE (default 0).  A context is not thread-safe: objects used from
+// several threads at once need their own (`Context::create()`).
 class Context {
  public:
   Context() {
@@ -162,10 +167,31 @@ class Context {
   void check(int rc, const char* what) const {
     if (rc != GICPB_OK) throw std::runtime_error(std::string(what) + ": " + gicpb_last_error(ctx_));
   }
+  static std::shared_ptr<Context> create() { return std::make_shared<Context>(); }
+  // the process-wide context (created on first use, destroyed at exit or by release_shared())
+  static std::shared_ptr<Context>& shared_slot() {
+    static std::shared_ptr<Context> slot;
+    return slot;
+  }
+  static std::shared_ptr<Context> shared() {
+    std::shared_ptr<Context>& slot = shared_slot();
+    if (!slot) slot = create();
+    return slot;
+  }
+  static void release_shared() { shared_slot().reset(); }
+  // The registration inputs (target / source index, covariances) inside the context belong to the object that set them
+  // last; an object that finds another owner sets its own inputs again before it solves.
+  const void* inputs_owner = nullptr;
 
  private:
   gicpb_ctx* ctx_ = nullptr;
 };
+
+inline Context* resolve(Context* given, std::shared_ptr<Context>& hold) {
+  if (given) return given;
+  hold = Context::shared();
+  return hold.get();
+}
 
 // pcl::transformPointCloud(in, out, tf): every field copied, xyz <- tf * xyz (reference src/GICPAlignment.cpp:146)
 inline void transformCloud(const Context& ctx, const CloudT& in, CloudT& out, const Mat4T& tf) {
@@ -184,11 +210,8 @@ template <class CloudPtr>
 inline void removeFromCloud(const CloudPtr& input_cloud, const CloudPtr& substract_cloud, double threshold,
                             const CloudPtr& cloud_filtered, Context* shared = nullptr) {
   log(kInfo, "Difference from segment with threshold: %f", threshold);
-  std::unique_ptr<Context> own;
-  if (!shared) {
-    own.reset(new Context);
-    shared = own.get();
-  }
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
   const int64_t n = (int64_t)input_cloud->points.size();
   std::vector<uint8_t> mask((size_t)n);
   int64_t kept = 0;
@@ -206,6 +229,68 @@ inline void removeFromCloud(const CloudPtr& input_cloud, const CloudPtr& substra
   out.height = 1;
   out.is_dense = true;
   *cloud_filtered = out;  // safe when cloud_filtered aliases input_cloud
+}
+
+// Utils::computeCloudResolution (reference src/Utils.cpp:145-174): mean distance to the 2nd nearest neighbour (the 1st
+// is the point itself) over the finite points
+template <class CloudPtr>
+inline double computeCloudResolution(const CloudPtr& cloud, Context* shared = nullptr) {
+  if (cloud->points.empty()) return 0.0;
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
+  double res = 0.0;
+  shared->check(gicpb_difference_set_subtract(shared->get(), &cloud->points[0].x, (int64_t)cloud->points.size(),
+                                              (int64_t)sizeof(cloud->points[0]), 0),
+                "gicpb_difference_set_subtract");  // the context's third index slot
+  shared->check(gicpb_cloud_resolution(shared->get(), 2, &res), "gicpb_cloud_resolution");
+  return res;
+}
+
+#ifndef GICPB_WITH_PCL
+struct alignas(16) Normal {  // memory layout of pcl::Normal
+  float normal_x = 0.f, normal_y = 0.f, normal_z = 0.f, pad_n_ = 0.f;
+  float curvature = 0.f, pad_c_[3] = {0.f, 0.f, 0.f};
+};
+static_assert(sizeof(Normal) == 32, "pcl::Normal is 32 bytes");
+struct PointCloudNormal {
+  typedef std::shared_ptr<PointCloudNormal> Ptr;
+  std::vector<Normal> points;
+  uint32_t width = 0, height = 1;
+  bool is_dense = true;
+  size_t size() const { return points.size(); }
+};
+typedef PointCloudNormal NormalCloudT;
+#else
+typedef pcl::PointCloud<pcl::Normal> NormalCloudT;
+#endif
+
+// Utils::getNormals (reference src/Utils.cpp:27-44): pcl::NormalEstimation with a radius search and the default viewpoint
+// (0, 0, 0); one normal per point (NaN x 4 where PCL gives none, is_dense then false).  Returns what the reference
+// returns: normals->size() == cloud->size().
+template <class CloudPtr, class NormalsPtr>
+inline bool getNormals(const CloudPtr& cloud, double normal_radius, const NormalsPtr& normals, Context* shared = nullptr) {
+  log(kInfo, "Computing normals with radius: %f", normal_radius);
+  std::shared_ptr<Context> hold;
+  shared = resolve(shared, hold);
+  const int64_t n = (int64_t)cloud->points.size();
+  normals->points.resize((size_t)n);
+  normals->width = (uint32_t)n;
+  normals->height = 1;
+  normals->is_dense = true;
+  if (n == 0) return true;
+  std::vector<float> out((size_t)n * 4);
+  int64_t finite = 0;
+  shared->check(gicpb_difference_set_subtract(shared->get(), &cloud->points[0].x, n, (int64_t)sizeof(cloud->points[0]), 0),
+                "gicpb_difference_set_subtract");  // the context's third index slot
+  shared->check(gicpb_normals(shared->get(), 2, normal_radius, out.data(), &finite), "gicpb_normals");
+  for (int64_t i = 0; i < n; ++i) {
+    normals->points[(size_t)i].normal_x = out[4 * (size_t)i];
+    normals->points[(size_t)i].normal_y = out[4 * (size_t)i + 1];
+    normals->points[(size_t)i].normal_z = out[4 * (size_t)i + 2];
+    normals->points[(size_t)i].curvature = out[4 * (size_t)i + 3];
+  }
+  normals->is_dense = finite == n;
+  return normals->points.size() == cloud->points.size();
 }
 
 }  // namespace gicpb_shim
@@ -226,13 +311,22 @@ class GICPAlignment {
       : transform_exists_(false), covariances_(use_covariances), fine_tf_(gicpb_shim::identity4()), max_iter_(100),
         tf_epsilon_(4e-3), max_corresp_distance_(4e-2), ransac_outlier_th_(1.0), target_cloud_(target_cloud),
         source_cloud_(source_cloud), aligned_cloud_(new PointCloudRGB), backup_cloud_(new PointCloudRGB),
-        converged_(false), fitness_(-1.0), inputs_set_(false), last_() {}
+        converged_(false), fitness_(-1.0), inputs_set_(false), tgt_indexed_(false), src_indexed_(false), last_(),
+        ctx_holder_(gicpb_shim::Context::shared()), ctx_(*ctx_holder_) {}
+  // the same, on a context of the caller's (one per thread when objects run concurrently)
+  GICPAlignment(CloudPtr target_cloud, CloudPtr source_cloud, bool use_covariances, std::shared_ptr<gicpb_shim::Context> context)
+      : transform_exists_(false), covariances_(use_covariances), fine_tf_(gicpb_shim::identity4()), max_iter_(100),
+        tf_epsilon_(4e-3), max_corresp_distance_(4e-2), ransac_outlier_th_(1.0), target_cloud_(target_cloud),
+        source_cloud_(source_cloud), aligned_cloud_(new PointCloudRGB), backup_cloud_(new PointCloudRGB),
+        converged_(false), fitness_(-1.0), inputs_set_(false), tgt_indexed_(false), src_indexed_(false), last_(),
+        ctx_holder_(context), ctx_(*ctx_holder_) {}
 
   ~GICPAlignment() {}
 
   bool transform_exists_;  // reference include/GICPAlignment.h:56
 
   void run() {  // :37-46
+    tgt_indexed_ = src_indexed_ = false;  // the caller may have edited the clouds since the last call
     configParameters();
     if (covariances_) applyCovariances();
     fineAlignment();
@@ -254,14 +348,10 @@ class GICPAlignment {
   void applyTFtoCloud(CloudPtr cloud) {  // :144-147
     gicpb_shim::transformCloud(ctx_, *cloud, *aligned_cloud_, fine_tf_);
   }
-  void setSourceCloud(CloudPtr source_cloud) {  // :166-169
-    source_cloud_ = source_cloud;
-    inputs_set_ = false;
-  }
-  void setTargetCloud(CloudPtr target_cloud) {  // :171-174
-    target_cloud_ = target_cloud;
-    inputs_set_ = false;
-  }
+  // :166-174: only the wrapper's pointers change.  gicp_ keeps the clouds given to setInputSource / setInputTarget by the
+  // last fineAlignment (:89-90), so a following iterate() still solves the OLD pair; the new cloud counts from the next run()
+  void setSourceCloud(CloudPtr source_cloud) { source_cloud_ = source_cloud; }
+  void setTargetCloud(CloudPtr target_cloud) { target_cloud_ = target_cloud; }
   void setMaxIterations(int iterations) {  // :176-180
     max_iter_ = iterations;
     configParameters();
@@ -286,7 +376,6 @@ class GICPAlignment {
 
  private:
   bool covariances_;
-  gicpb_shim::Context ctx_;  // replaces the pcl::GeneralizedIterativeClosestPoint member gicp_ (GICPAlignment.h:153)
   Matrix4f fine_tf_;
   int max_iter_;
   double tf_epsilon_;
@@ -295,8 +384,13 @@ class GICPAlignment {
   CloudPtr target_cloud_, source_cloud_, aligned_cloud_, backup_cloud_;
   bool converged_;
   double fitness_;
-  bool inputs_set_;
+  bool inputs_set_;                 // gicp_ holds input clouds (set by the last fineAlignment)
+  bool tgt_indexed_, src_indexed_;  // within one run(): the context's index of that cloud is current
+  CloudPtr input_target_, input_source_;  // what gicp_.setInputTarget / setInputSource were given (:89-90)
   gicpb_align_result last_;
+  // replaces the pcl::GeneralizedIterativeClosestPoint member gicp_ (GICPAlignment.h:153)
+  std::shared_ptr<gicpb_shim::Context> ctx_holder_;
+  gicpb_shim::Context& ctx_;
 
   void configParameters() {  // :48-54
     gicpb_params p;
@@ -307,13 +401,30 @@ class GICPAlignment {
     ctx_.check(gicpb_set_params(ctx_.get(), &p), "gicpb_set_params");
   }
 
+  void indexCloud(int which, const CloudPtr& cloud) {
+    if (cloud->points.empty()) throw std::runtime_error("empty cloud");
+    const int rc = which == 0 ? gicpb_set_target(ctx_.get(), &cloud->points[0].x, (int64_t)cloud->points.size(),
+                                                 (int64_t)sizeof(cloud->points[0]), 0)
+                              : gicpb_set_source(ctx_.get(), &cloud->points[0].x, (int64_t)cloud->points.size(),
+                                                 (int64_t)sizeof(cloud->points[0]), 0);
+    ctx_.check(rc, which == 0 ? "gicpb_set_target" : "gicpb_set_source");
+    ctx_.inputs_owner = this;
+    (which == 0 ? tgt_indexed_ : src_indexed_) = true;
+  }
+  void ensureIndexed() {  // index only (no kNN-20 covariances): all the resolution and the normals need
+    if (ctx_.inputs_owner != this) tgt_indexed_ = src_indexed_ = false;
+    if (!tgt_indexed_) indexCloud(0, target_cloud_);
+    if (!src_indexed_) indexCloud(1, source_cloud_);
+  }
+
   // :56-71 for one cloud.  Both resolutions are recomputed on every call, as upstream does.  The radius-search normals
   // only decide WHICH points survive: pcl::NormalEstimation gives NaN to a point with fewer than 3 points inside the
   // radius, removeNaNNormalsFromPointCloud + Filter::extractIndices then drop it from the CALLER's cloud (:63-67).  The
   // covariances built from the normals (:70) are reset by setInputSource / setInputTarget in PCL 1.8.1 (:89-90,
-  // SURVEY App. A.1) and never reach the solver, so they are not built.
+  // SURVEY App. A.1) and never reach the solver, so they are not built.  A cloud is indexed again only after it lost
+  // points: one run() with use_covariances builds 2 indices when nothing is dropped, at most 4.
   void getCovariances(CloudPtr cloud, bool is_source) {
-    setInputs();
+    ensureIndexed();
     double target_res = 0, source_res = 0;
     ctx_.check(gicpb_cloud_resolution(ctx_.get(), 0, &target_res), "gicpb_cloud_resolution");
     ctx_.check(gicpb_cloud_resolution(ctx_.get(), 1, &source_res), "gicpb_cloud_resolution");
@@ -330,7 +441,7 @@ class GICPAlignment {
       cloud->points.resize(w);
       cloud->width = (uint32_t)w;
       cloud->height = 1;
-      inputs_set_ = false;
+      (is_source ? src_indexed_ : tgt_indexed_) = false;
     }
   }
 
@@ -340,20 +451,32 @@ class GICPAlignment {
     getCovariances(target_cloud_, false);
   }
 
-  void setInputs() {  // gicp_.setInputSource / setInputTarget, :89-90
-    if (source_cloud_->points.empty() || target_cloud_->points.empty()) throw std::runtime_error("empty cloud");
-    // both uploads go to the copy stream, target first: the source uploads while the target is being indexed; then
-    // one call indexes both clouds and computes their covariances (the target's beside the source's index build)
-    ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 0, &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
-                                    (int64_t)sizeof(target_cloud_->points[0])),
-               "gicpb_prefetch_cloud");
-    ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 1, &source_cloud_->points[0].x, (int64_t)source_cloud_->points.size(),
-                                    (int64_t)sizeof(source_cloud_->points[0])),
-               "gicpb_prefetch_cloud");
-    ctx_.check(gicpb_set_clouds(ctx_.get(), &target_cloud_->points[0].x, (int64_t)target_cloud_->points.size(),
-                                (int64_t)sizeof(target_cloud_->points[0]), &source_cloud_->points[0].x,
-                                (int64_t)source_cloud_->points.size(), (int64_t)sizeof(source_cloud_->points[0]), 0),
-               "gicpb_set_clouds");
+  // gicp_.setInputSource / setInputTarget (:89-90) + the index builds and kNN-20 covariances PCL's align() starts with
+  void setInputs(const CloudPtr& target, const CloudPtr& source, bool reuse_indices) {
+    if (source->points.empty() || target->points.empty()) throw std::runtime_error("empty cloud");
+    if (ctx_.inputs_owner != this) tgt_indexed_ = src_indexed_ = false;
+    if (reuse_indices && (tgt_indexed_ || src_indexed_)) {
+      // applyCovariances has just indexed these very clouds: index what changed since, then the covariances
+      ensureIndexed();
+      ctx_.check(gicpb_compute_covariances(ctx_.get()), "gicpb_compute_covariances");
+    } else {
+      // both uploads go to the copy stream, target first: the source uploads while the target is being indexed; then
+      // one call indexes both clouds and computes their covariances (the target's beside the source's index build)
+      ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 0, &target->points[0].x, (int64_t)target->points.size(),
+                                      (int64_t)sizeof(target->points[0])),
+                 "gicpb_prefetch_cloud");
+      ctx_.check(gicpb_prefetch_cloud(ctx_.get(), 1, &source->points[0].x, (int64_t)source->points.size(),
+                                      (int64_t)sizeof(source->points[0])),
+                 "gicpb_prefetch_cloud");
+      ctx_.check(gicpb_set_clouds(ctx_.get(), &target->points[0].x, (int64_t)target->points.size(),
+                                  (int64_t)sizeof(target->points[0]), &source->points[0].x, (int64_t)source->points.size(),
+                                  (int64_t)sizeof(source->points[0]), 0),
+                 "gicpb_set_clouds");
+    }
+    ctx_.inputs_owner = this;
+    tgt_indexed_ = src_indexed_ = true;
+    input_target_ = target;
+    input_source_ = source;
     inputs_set_ = true;
   }
 
@@ -367,7 +490,7 @@ class GICPAlignment {
 
   void fineAlignment() {  // :86-109
     gicpb_shim::log(gicpb_shim::kInfo, "Perform GICP with %d iterations", max_iter_);
-    setInputs();
+    setInputs(target_cloud_, source_cloud_, true);
     const auto begin = std::chrono::steady_clock::now();
     gicpb_shim::log(gicpb_shim::kInfo, "This step may take a while ...");
     align();
@@ -386,7 +509,14 @@ class GICPAlignment {
   void iterateFineAlignment(CloudPtr cloud) {  // :111-127
     backUp(cloud);
     gicpb_shim::log(gicpb_shim::kInfo, "Computing iteration...");
-    if (!inputs_set_) setInputs();
+    if (!inputs_set_) {  // gicp_.align() without input clouds: PCL's initCompute fails, nothing converges, `cloud` is untouched
+      converged_ = false;
+      gicpb_shim::log(gicpb_shim::kError, "GICP no converge");
+      return;
+    }
+    // gicp_ still holds the clouds of the last fineAlignment, whatever setSourceCloud / setTargetCloud were given since;
+    // if another object used the shared context in between, they are set again (the clouds are held by pointer, as in PCL)
+    if (ctx_.inputs_owner != this) setInputs(input_target_, input_source_, false);
     align();  // PCL's align() restarts from the stored input source at identity
     const Matrix4f temp_tf = gicpb_shim::from_row_major(last_.transform);
     if (converged_) {
@@ -397,7 +527,7 @@ class GICPAlignment {
       gicpb_shim::log(gicpb_shim::kError, "GICP no converge");
     }
     // align(*cloud) overwrites `cloud` with final_transformation * input source
-    gicpb_shim::transformCloud(ctx_, *source_cloud_, *cloud, temp_tf);
+    gicpb_shim::transformCloud(ctx_, *input_source_, *cloud, temp_tf);
   }
 
   void backUp(CloudPtr cloud) { *backup_cloud_ = *cloud; }  // :134-137

@@ -163,6 +163,14 @@ int gicpb_cloud_resolution(gicpb_ctx* ctx, int which, double* resolution);
  * valid is a host array in ORIGINAL point order. */
 int gicpb_normal_validity(gicpb_ctx* ctx, int which, double radius, uint8_t* valid, int64_t* n_valid);
 
+/* Utils::getNormals (src/Utils.cpp:27-44): pcl::NormalEstimation<PointXYZRGB, Normal> with setRadiusSearch(radius) on an
+ * indexed cloud (which: 0 target, 1 source, 2 subtract), viewpoint (0, 0, 0).  normals4[4 i .. 4 i + 3] = normal_x, normal_y,
+ * normal_z, curvature of point i (original order): the eigenvector of the smallest eigenvalue of the neighbourhood's
+ * covariance - accumulated in float over the neighbours sorted by (distance, index), as PCL 1.8.1 does - flipped towards
+ * the viewpoint, and |lambda_0 / trace|.  NaN x 4 for a non-finite point and for fewer than 3 points inside the radius
+ * (exactly the points gicpb_normal_validity marks 0).  *n_valid = number of finite normals.  Host output. */
+int gicpb_normals(gicpb_ctx* ctx, int which, double radius, float* normals4, int64_t* n_valid);
+
 /* ---- the callers either side of the registration path ---------------------------------------
  * FODDetector::clusterPossibleFODs (src/FODDetector.cpp:45-58 -> pcl::EuclideanClusterExtraction::extract, called at
  * src/LeicaStateMachine.cpp:200-205 on the difference cloud): connected components of the graph joining two points

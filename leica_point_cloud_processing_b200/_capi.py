@@ -140,6 +140,7 @@ _SIGNATURES = [
     ("gicpb_bench_kernel", ctypes.c_int, [_VOID_P, ctypes.c_int, c_float_p, ctypes.c_int, c_double_p, c_int64_p]),
     ("gicpb_cloud_resolution", ctypes.c_int, [_VOID_P, ctypes.c_int, c_double_p]),
     ("gicpb_normal_validity", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.c_double, c_uint8_p, c_int64_p]),
+    ("gicpb_normals", ctypes.c_int, [_VOID_P, ctypes.c_int, ctypes.c_double, c_float_p, c_int64_p]),
     ("gicpb_euclidean_clusters", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
                                                 ctypes.c_double, ctypes.c_int64, ctypes.c_int64, c_int32_p, c_int64_p]),
     ("gicpb_voxel_grid", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_double,
@@ -558,6 +559,15 @@ class Engine:
         self._check(self.lib.gicpb_normal_validity(self.h, which, float(radius), mask.ctypes.data_as(c_uint8_p),
                                                    ctypes.byref(kept)))
         return mask, int(kept.value)
+
+    def normals(self, which, radius):
+        """Utils::getNormals of an indexed cloud: (float32 [n, 4] = nx, ny, nz, curvature with NaN rows where PCL gives no
+        normal, number of finite normals)."""
+        n = self.grid_info(which)["n_points"]
+        out = np.empty((n, 4), np.float32)
+        kept = ctypes.c_int64()
+        self._check(self.lib.gicpb_normals(self.h, which, float(radius), out.ctypes.data_as(c_float_p), ctypes.byref(kept)))
+        return out, int(kept.value)
 
     def stream_handle(self):
         """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(handle) wraps it)."""

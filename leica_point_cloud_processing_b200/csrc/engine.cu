@@ -738,6 +738,47 @@ GridIndex& pick_grid(gicpb_ctx* c, int which) {
   throw ArgError("which must be 0 (target), 1 (source) or 2 (subtract)");
 }
 
+// Utils::getNormals on an indexed cloud: (nx, ny, nz, curvature) per point in ORIGINAL order into c->io_b (float4 rows, NaN x 4
+// where PCL gives no normal); returns the number of finite normals, *total_points = rows written
+int64_t compute_normals(gicpb_ctx* c, int which, double radius, int64_t* total_points) {
+  if (!(radius > 0)) throw ArgError("radius must be > 0");
+  GridIndex& g = pick_grid(c, which);
+  if (!g.ready()) throw StateError("cloud not set");
+  const int64_t total = g.n_points();
+  const int n = g.n_indexed();
+  const float r2 = (float)(radius * radius);  // KdTreeFLANN::radiusSearch: float(radius * radius), d2 < r2
+  DevBuf<unsigned> counts, offsets, scan_tmp;
+  counts.reserve((size_t)n + 1);
+  offsets.reserve((size_t)n + 1);
+  scan_tmp.reserve(scan_tmp_entries(n + 1));
+  // counts[n] = 0, so that the exclusive scan leaves the total in offsets[n]
+  GICPB_CUDA(cudaMemsetAsync(counts.get() + n, 0, sizeof(unsigned), c->stream));
+  launch_radius_counts(g.view(), r2, counts.get(), far_work(c, n), c->stream);
+  exclusive_scan_u32(counts.get(), offsets.get(), (int64_t)n + 1, scan_tmp.get(), c->stream);
+  GICPB_CUDA(cudaMemsetAsync(c->counter.get(), 0, sizeof(unsigned long long), c->stream));
+  launch_sum_counts(counts.get(), n, c->counter.get(), c->stream);
+  unsigned total_keys = 0;
+  unsigned long long total_wide = 0;
+  GICPB_CUDA(cudaMemcpyAsync(&total_keys, offsets.get() + n, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  GICPB_CUDA(cudaMemcpyAsync(&total_wide, c->counter.get(), sizeof(total_wide), cudaMemcpyDeviceToHost, c->stream));
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (total_wide != (unsigned long long)total_keys)
+    throw ArgError("normal radius too large: more than 2^32 neighbour entries (" + std::to_string(total_wide) + ")");
+  DevBuf<unsigned long long> keys;
+  keys.reserve((size_t)total_keys + 1);
+  launch_radius_fill(g.view(), r2, offsets.get(), keys.get(), far_work(c, n), c->stream);
+  c->io_b.reserve((size_t)total * 16);
+  GICPB_CUDA(cudaMemsetAsync(c->io_b.get(), 0xff, (size_t)total * 16, c->stream));  // all-ones = a quiet NaN: no normal
+  GICPB_CUDA(cudaMemsetAsync(c->counter.get(), 0, sizeof(unsigned long long), c->stream));
+  launch_normals_solve(g.view(), counts.get(), offsets.get(), keys.get(), reinterpret_cast<float4*>(c->io_b.get()),
+                       c->counter.get(), c->stream);
+  unsigned long long kept = 0;
+  GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  *total_points = total;
+  return (int64_t)kept;
+}
+
 }  // namespace
 
 // ---- C ABI ---------------------------------------------------------------------------------------------------
@@ -1336,23 +1377,30 @@ int gicpb_cloud_resolution(gicpb_ctx* c, int which, double* resolution) {
   });
 }
 
+// pcl::removeNaNNormalsFromPointCloud keeps a point iff all three components of its normal are finite.  That is "at least 3
+// points inside the radius" almost always - but a neighbourhood whose float moments cancel to a zero covariance (a cloud far
+// from the origin) gives 0 / 0 inside pcl::eigen33, and PCL drops that point too: the mask comes from the normals themselves.
 int gicpb_normal_validity(gicpb_ctx* c, int which, double radius, uint8_t* valid, int64_t* n_valid) {
   return guarded(c, [&] {
     if (!valid) throw ArgError("null output");
-    if (!(radius > 0)) throw ArgError("radius must be > 0");
-    GridIndex& g = pick_grid(c, which);
-    if (!g.ready()) throw StateError("cloud not set");
-    const int64_t total = g.n_points();
-    c->io_b.reserve((size_t)total);
-    GICPB_CUDA(cudaMemsetAsync(c->io_b.get(), 0, (size_t)total, c->stream));  // non-finite points: no normal
-    GICPB_CUDA(cudaMemsetAsync(c->counter.get(), 0, sizeof(unsigned long long), c->stream));
-    launch_radius_count(g.view(), (float)(radius * radius), 3, c->io_b.get(), c->counter.get(), far_work(c, g.n_indexed()),
-                        c->stream);
-    unsigned long long kept = 0;
-    GICPB_CUDA(cudaMemcpyAsync(&kept, c->counter.get(), sizeof(kept), cudaMemcpyDeviceToHost, c->stream));
-    GICPB_CUDA(cudaMemcpyAsync(valid, c->io_b.get(), (size_t)total, cudaMemcpyDeviceToHost, c->stream));
-    GICPB_CUDA(cudaStreamSynchronize(c->stream));
-    if (n_valid) *n_valid = (int64_t)kept;
+    int64_t total = 0;
+    const int64_t kept = compute_normals(c, which, radius, &total);
+    std::vector<float> rows((size_t)total * 4);
+    download_bytes(c, rows.data(), c->io_b.get(), (size_t)total * 16);
+    for (int64_t i = 0; i < total; ++i)
+      valid[i] = (std::isfinite(rows[4 * (size_t)i]) && std::isfinite(rows[4 * (size_t)i + 1]) &&
+                  std::isfinite(rows[4 * (size_t)i + 2])) ? 1 : 0;
+    if (n_valid) *n_valid = kept;
+  });
+}
+
+int gicpb_normals(gicpb_ctx* c, int which, double radius, float* normals4, int64_t* n_valid) {
+  return guarded(c, [&] {
+    if (!normals4) throw ArgError("null output");
+    int64_t total = 0;
+    const int64_t kept = compute_normals(c, which, radius, &total);
+    download_bytes(c, normals4, c->io_b.get(), (size_t)total * 16);
+    if (n_valid) *n_valid = kept;
   });
 }
 

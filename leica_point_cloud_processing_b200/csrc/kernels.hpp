@@ -92,14 +92,23 @@ void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const 
 void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, int64_t stride, float thr_next,
                        bool always_keep, unsigned char* mask, unsigned long long* kept, const FarWork& fw,
                        cudaStream_t stream);
-// use_covariances branch: points with >= need neighbours inside sqrt(r2) (valid[] in ORIGINAL order; non-indexed points
-// must be pre-set to 0 by the caller), and the mean 2nd-neighbour distance sums (partials sized like the fitness ones)
-void launch_radius_count(const GridView& g, float r2, int need, unsigned char* valid, unsigned long long* kept,
-                         const FarWork& fw, cudaStream_t stream);
+// use_covariances branch: the mean 2nd-neighbour distance sums (partials sized like the fitness ones); the normals: normals.cu
 void launch_resolution(const GridView& g, double* partials, double* out2, const FarWork& fw, cudaStream_t stream);
 void launch_transform(const unsigned char* in, unsigned char* out, int64_t n, int64_t stride, const Rigid& T,
                       cudaStream_t stream);
 void launch_pack_queries(const unsigned char* raw, int64_t n, int64_t stride, float4* out, cudaStream_t stream);
+
+// ---- normals.cu ---------------------------------------------------------------------------------------
+// Utils::getNormals (pcl::NormalEstimation, radius search): counts[i] = neighbours (d2 < r2, the point included) of sorted
+// point i; after an exclusive scan of the counts, fill writes every point's keys (d2 bits << 32 | original index) at
+// keys[offsets[i] ...]; solve sorts each list and writes (nx, ny, nz, curvature) - NaN x 4 below 3 neighbours - to
+// out4[ORIGINAL index] (entries of non-indexed points must be pre-set to NaN) and adds the finite count to *kept.
+void launch_radius_counts(const GridView& g, float r2, unsigned* counts, const FarWork& fw, cudaStream_t stream);
+void launch_sum_counts(const unsigned* counts, int n, unsigned long long* out, cudaStream_t stream);  // *out += sum, 64 bits
+void launch_radius_fill(const GridView& g, float r2, const unsigned* offsets, unsigned long long* keys, const FarWork& fw,
+                        cudaStream_t stream);
+void launch_normals_solve(const GridView& g, const unsigned* counts, const unsigned* offsets, unsigned long long* keys,
+                          float4* out4, unsigned long long* kept, cudaStream_t stream);
 
 // ---- knn_cov.cu ---------------------------------------------------------------------------------------
 // self-kNN (k <= 32) of sorted points [lo, hi) of grid g + regularised covariance normal per point.

@@ -281,69 +281,7 @@ __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) difference_kernel(Gr
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, (unsigned long long)mine);
 }
 
-// ---- the use_covariances branch of the reference (src/GICPAlignment.cpp:56-71) ------------------------------------------
-// counts the points closer than sqrt(r2) (strictly, as FLANN's radius search) up to `need`
-struct CountVisitor {
-  const float4* pts;
-  float qx, qy, qz;
-  float r2;
-  int need, count;
-  __device__ __forceinline__ float bound() const { return r2; }
-  __device__ __forceinline__ bool apply(const float4& p) {
-    count += dist2(qx, qy, qz, p) < r2 ? 1 : 0;
-    return count >= need;
-  }
-  __device__ __forceinline__ bool point(unsigned i) { return apply(__ldg(&pts[i])); }
-  __device__ __forceinline__ bool point2(unsigned i, bool two) {
-    const float4 p0 = __ldg(&pts[i]);
-    const float4 p1 = __ldg(&pts[two ? i + 1 : i]);
-    bool stop = apply(p0);
-    if (two) stop = apply(p1) || stop;
-    return stop;
-  }
-  __device__ __forceinline__ bool range(unsigned b, unsigned e) {
-    for (unsigned i = b; i < e; ++i)
-      if (point(i)) return true;
-    return false;
-  }
-};
-
-// valid[original index] = 1 iff the sorted point has >= need points (itself included) inside the radius: what
-// pcl::NormalEstimation needs for a finite normal (Utils::getNormals, reference src/Utils.cpp:27-44)
-template <bool kFar>
-__global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) radius_count_kernel(GridView g, float r2, int need,
-                                                                                 unsigned char* __restrict__ valid,
-                                                                                 unsigned long long* __restrict__ kept,
-                                                                                 FarWork fw) {
-  GICPB_NEAR_QUEUE();
-  unsigned mine = 0;
-  auto body = [&](int i) {
-    const float4 p = __ldg(&g.pts[i]);
-    const Query q = make_query(g, p.x, p.y, p.z);
-    CountVisitor v{g.pts, p.x, p.y, p.z, r2, need, 0};
-    if (kFar) {
-      far_search(g, q, v);
-    } else {
-      const float rad = fadd(sqrt_up(r2), g.margin);
-      const int x0 = max(cell_of(fsub(p.x, rad), g.ox, g.inv_h), 0), x1 = min(cell_of(fadd(p.x, rad), g.ox, g.inv_h), g.nx - 1);
-      const int y0 = max(cell_of(fsub(p.y, rad), g.oy, g.inv_h), 0), y1 = min(cell_of(fadd(p.y, rad), g.oy, g.inv_h), g.ny - 1);
-      const int z0 = max(cell_of(fsub(p.z, rad), g.oz, g.inv_h), 0), z1 = min(cell_of(fadd(p.z, rad), g.oz, g.inv_h), g.nz - 1);
-      if ((long long)(y1 - y0 + 1) * (z1 - z0 + 1) > kMaxBoxRows) {
-        fw.flags[i] = 1;
-        return;
-      }
-      QueueVisitor<kNnThreads, kQueueCap, CountVisitor> qv{qb, qe, 0, v};
-      if (!visit_box(g, q, x0, x1, y0, y1, z0, z1, qv)) qv.drain();
-    }
-    const bool ok = v.count >= need;
-    valid[__float_as_int(p.w)] = ok ? 1 : 0;
-    mine += ok ? 1u : 0u;
-  };
-  GICPB_RUN_ITEMS(g.n, body)
-  mine = __reduce_add_sync(kFullMask, mine);
-  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(kept, (unsigned long long)mine);
-}
-
+// ---- the use_covariances branch of the reference (src/GICPAlignment.cpp:56-71): the resolution here, the normals in normals.cu ----
 // sum over the indexed points of sqrt(d2 to the 2nd nearest neighbour) (the point itself is the 1st) and their count:
 // Utils::computeCloudResolution, reference src/Utils.cpp:145-174.  partials[(row0 + block)*2 + {0,1}]
 template <bool kFar>
@@ -502,16 +440,6 @@ void launch_difference(const GridView& g, const unsigned char* raw, int64_t n, i
   GICPB_LAUNCHED();
   difference_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, raw, n, stride, thr_next, always_keep ? 1 : 0,
                                                                     mask, kept, fw);
-  GICPB_LAUNCHED();
-}
-
-void launch_radius_count(const GridView& g, float r2, int need, unsigned char* valid, unsigned long long* kept,
-                         const FarWork& fw, cudaStream_t stream) {
-  if (g.n <= 0) return;
-  reset_far(fw, g.n, stream);
-  radius_count_kernel<false><<<nblocks(g.n, kNnThreads), kNnThreads, 0, stream>>>(g, r2, need, valid, kept, fw);
-  GICPB_LAUNCHED();
-  radius_count_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, r2, need, valid, kept, fw);
   GICPB_LAUNCHED();
 }
 

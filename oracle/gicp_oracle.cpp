@@ -1385,18 +1385,169 @@ double orc_resolution(const float* xyz, int n) {
 // radius search yields NaN for a non-finite point and for a point with fewer than 3 neighbours (itself included)
 // inside the radius; GICPAlignment::getCovariances then drops exactly those points from the caller's cloud
 // (reference src/GICPAlignment.cpp:63-67).  mask[i] = 1 iff the normal of point i is finite.  Returns the count.
+int orc_normals(const float* xyz, int n, double radius, float* out4);
 int orc_normal_validity(const float* xyz, int n, double radius, unsigned char* mask) {
-  KdTree tree(xyz, n);
-  const float r2 = (float)(radius * radius);
+  // pcl::removeNaNNormalsFromPointCloud: a point stays iff normal_x, normal_y and normal_z are finite - which is "at least 3
+  // points inside the radius" except where the float moments cancel to a zero covariance (then pcl::eigen33 divides 0 by 0)
+  std::vector<float> nrm((size_t)std::max(n, 1) * 4);
+  orc_normals(xyz, n, radius, nrm.data());
   int kept = 0;
-#ifdef _OPENMP
-#pragma omp parallel for reduction(+ : kept) schedule(dynamic, 1024)
-#endif
   for (int i = 0; i < n; ++i) {
-    const float* p = xyz + 3 * i;
-    const bool ok = std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && tree.count_within(p, r2, 3) >= 3;
+    const float* o = &nrm[4 * (size_t)i];
+    const bool ok = std::isfinite(o[0]) && std::isfinite(o[1]) && std::isfinite(o[2]);
     mask[i] = ok ? 1 : 0;
     kept += ok ? 1 : 0;
+  }
+  return kept;
+}
+
+// ---- Utils::getNormals (reference src/Utils.cpp:27-44) = pcl::NormalEstimation<PointXYZRGB, Normal> with a radius search,
+//      restated from PCL 1.8.1 features/normal_3d.h(pp), common/impl/centroid.hpp and common/impl/eigen.hpp:
+//        * neighbours = FLANN radiusSearch, d2 < float(radius^2), SORTED by (d2, index) (KdTreeFLANN sorted_ = true);
+//        * computeMeanAndCovarianceMatrix with Scalar = float: nine FLOAT accumulators over the neighbours in that order
+//          (xx xy xz yy yz zz x y z), divided by the count, cov = E[ab] - E[a]E[b];
+//        * solvePlaneParameters: pcl::eigen33 (matrix scaled by its largest |entry|, closed-form roots of the
+//          characteristic polynomial in float, eigenvector of the smallest root = the longest of the three row cross
+//          products of A - lambda I), curvature = |lambda / trace|;
+//        * flipNormalTowardsViewpoint with the default viewpoint (0, 0, 0).
+//      A non-finite point, or one with fewer than 3 neighbours (itself included), gets NaN x 4.
+//      out4: nx ny nz curvature per point.  Returns the number of finite normals.
+namespace {
+void roots2_f(float b, float c, float roots[3]) {
+  roots[0] = 0.f;
+  float d = (float)(b * b - 4.0 * c);
+  if (d < 0.0) d = 0.0;
+  const float sd = std::sqrt(d);
+  roots[2] = 0.5f * (b + sd);
+  roots[1] = 0.5f * (b - sd);
+}
+void roots3_f(const float m[9], float roots[3]) {
+  const float c0 = m[0] * m[4] * m[8] + 2.f * m[1] * m[2] * m[5] - m[0] * m[5] * m[5] - m[4] * m[2] * m[2] - m[8] * m[1] * m[1];
+  const float c1 = m[0] * m[4] - m[1] * m[1] + m[0] * m[8] - m[2] * m[2] + m[4] * m[8] - m[5] * m[5];
+  const float c2 = m[0] + m[4] + m[8];
+  if (std::fabs(c0) < std::numeric_limits<float>::epsilon()) {
+    roots2_f(c2, c1, roots);
+    return;
+  }
+  const float s_inv3 = (float)(1.0 / 3.0);
+  const float s_sqrt3 = std::sqrt(3.0f);
+  const float c2_over_3 = c2 * s_inv3;
+  float a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+  if (a_over_3 > 0.f) a_over_3 = 0.f;
+  const float half_b = 0.5f * (c0 + c2_over_3 * (2.f * c2_over_3 * c2_over_3 - c1));
+  float q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+  if (q > 0.f) q = 0.f;
+  const float rho = std::sqrt(-a_over_3);
+  const float theta = std::atan2(std::sqrt(-q), half_b) * s_inv3;
+  const float cos_theta = std::cos(theta), sin_theta = std::sin(theta);
+  roots[0] = c2_over_3 + 2.f * rho * cos_theta;
+  roots[1] = c2_over_3 - rho * (cos_theta + s_sqrt3 * sin_theta);
+  roots[2] = c2_over_3 - rho * (cos_theta - s_sqrt3 * sin_theta);
+  if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  if (roots[1] >= roots[2]) {
+    std::swap(roots[1], roots[2]);
+    if (roots[0] >= roots[1]) std::swap(roots[0], roots[1]);
+  }
+  if (roots[0] <= 0.f) roots2_f(c2, c1, roots);
+}
+}  // namespace
+
+int orc_normals(const float* xyz, int n, double radius, float* out4) {
+  KdTree tree(xyz, n);
+  const float r2 = (float)(radius * radius);
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  int kept = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : kept) schedule(dynamic, 256)
+#endif
+  for (int i = 0; i < n; ++i) {
+    float* o = out4 + 4 * (size_t)i;
+    o[0] = o[1] = o[2] = o[3] = nan;
+    const float* p = xyz + 3 * i;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) continue;
+    std::vector<int> nn;
+    tree.radius(p, r2, nn);
+    if (nn.size() < 3) continue;
+    std::vector<std::pair<float, int>> order;
+    order.reserve(nn.size());
+    for (int j : nn) order.emplace_back(sqdist(p, xyz + 3 * j), j);
+    std::sort(order.begin(), order.end());
+    float accu[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (const auto& e : order) {
+      const float* c = xyz + 3 * e.second;
+      accu[0] += c[0] * c[0];
+      accu[1] += c[0] * c[1];
+      accu[2] += c[0] * c[2];
+      accu[3] += c[1] * c[1];
+      accu[4] += c[1] * c[2];
+      accu[5] += c[2] * c[2];
+      accu[6] += c[0];
+      accu[7] += c[1];
+      accu[8] += c[2];
+    }
+    const float cntf = (float)order.size();
+    for (int k = 0; k < 9; ++k) accu[k] /= cntf;
+    float m[9];
+    m[0] = accu[0] - accu[6] * accu[6];
+    m[1] = accu[1] - accu[6] * accu[7];
+    m[2] = accu[2] - accu[6] * accu[8];
+    m[4] = accu[3] - accu[7] * accu[7];
+    m[5] = accu[4] - accu[7] * accu[8];
+    m[8] = accu[5] - accu[8] * accu[8];
+    m[3] = m[1];
+    m[6] = m[2];
+    m[7] = m[5];
+    // pcl::eigen33(mat, eigenvalue, eigenvector)
+    float scale = 0.f;
+    for (int k = 0; k < 9; ++k) scale = std::max(scale, std::fabs(m[k]));
+    if (scale <= std::numeric_limits<float>::min()) scale = 1.f;
+    float sm[9];
+    for (int k = 0; k < 9; ++k) sm[k] = m[k] / scale;
+    float roots[3];
+    roots3_f(sm, roots);
+    const float eigenvalue = roots[0] * scale;
+    sm[0] -= roots[0];
+    sm[4] -= roots[0];
+    sm[8] -= roots[0];
+    auto cross = [](const float* a, const float* b, float* c) {
+      c[0] = a[1] * b[2] - a[2] * b[1];
+      c[1] = a[2] * b[0] - a[0] * b[2];
+      c[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    float v1[3], v2[3], v3[3];
+    cross(sm, sm + 3, v1);
+    cross(sm, sm + 6, v2);
+    cross(sm + 3, sm + 6, v3);
+    const float l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2];
+    const float l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2];
+    const float l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+    const float* v = v3;
+    float len = l3;
+    if (l1 >= l2 && l1 >= l3) {
+      v = v1;
+      len = l1;
+    } else if (l2 >= l1 && l2 >= l3) {
+      v = v2;
+      len = l2;
+    }
+    const float s = std::sqrt(len);
+    float nx = v[0] / s, ny = v[1] / s, nz = v[2] / s;
+    const float eig_sum = m[0] + m[4] + m[8];
+    const float curvature = eig_sum != 0.f ? std::fabs(eigenvalue / eig_sum) : 0.f;
+    // flipNormalTowardsViewpoint(point, 0, 0, 0, ...)
+    const float vx = 0.f - p[0], vy = 0.f - p[1], vz = 0.f - p[2];
+    const float cos_theta = vx * nx + vy * ny + vz * nz;
+    if (cos_theta < 0) {
+      nx *= -1;
+      ny *= -1;
+      nz *= -1;
+    }
+    o[0] = nx;
+    o[1] = ny;
+    o[2] = nz;
+    o[3] = curvature;
+    // a covariance that cancelled to zero gives 0 / 0 above: the normal is NaN although the point has neighbours
+    kept += (std::isfinite(nx) && std::isfinite(ny) && std::isfinite(nz)) ? 1 : 0;
   }
   return kept;
 }

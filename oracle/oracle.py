@@ -221,6 +221,14 @@ class Oracle:
                                          _p(mask, c_ubyte_p))
         return mask, int(n)
 
+    def normals(self, xyz, radius):
+        """Utils::getNormals: float32 [n, 4] (nx, ny, nz, curvature; NaN where PCL gives no normal) and the finite count"""
+        a = _xyz(xyz)
+        out = np.empty((len(a), 4), np.float32)
+        self.lib.orc_normals.restype = ctypes.c_int
+        n = self.lib.orc_normals(_p(a, c_float_p), ctypes.c_int(len(a)), ctypes.c_double(radius), _p(out, c_float_p))
+        return out, int(n)
+
     def euclidean_clusters(self, xyz, tolerance, min_size=1, max_size=0):
         """pcl::EuclideanClusterExtraction::extract: (labels in PCL's cluster order, -1 = none; n_clusters)"""
         a = _xyz(xyz) if len(xyz) else np.zeros((0, 3), np.float32)

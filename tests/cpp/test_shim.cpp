@@ -248,6 +248,61 @@ int main(int argc, char** argv) {
     }
   }
 
+  if (argc > 5) {
+    // The stages of one LeicaStateMachine run in the reference's order (src/LeicaStateMachine.cpp:61-65,138-216; the
+    // "drops in unchanged" test is test/test_state_machine.cpp:70-78), every stage through its shim, all on the one
+    // shared context: downsample both clouds -> GICP -> transform the source -> removeFromCloud -> FODDetector.
+    // argv[4]: a panel scan (offset pose, FOD blobs on it), argv[5]: the CAD cloud.  InitialAlignment is out of scope:
+    // the offset is small enough for GICP alone.
+    CloudPtr scan = load(argv[4]), cad = load(argv[5]);
+    const double leaf_size_factor = 10;
+    const double target_res = gicpb_shim::computeCloudResolution(cad);
+    const double source_res = gicpb_shim::computeCloudResolution(scan);
+    const double leaf_size = leaf_size_factor * std::max(target_res, source_res);
+    CloudPtr source_f(new PointCloudRGB), target_f(new PointCloudRGB);
+    gicpb_shim::downsampleCloud(scan, source_f, leaf_size);
+    gicpb_shim::downsampleCloud(cad, target_f, leaf_size);
+    std::printf("RESULT pipeline_resolution %.12g %.12g\n", target_res, source_res);
+    std::printf("RESULT pipeline_downsampled %zu %zu\n", source_f->points.size(), target_f->points.size());
+    GICPAlignment gicp_alignment(target_f, source_f, false);
+    gicp_alignment.setMaxCorrespondenceDistance(1);
+    gicp_alignment.run();
+    CloudPtr aligned_cloud(new PointCloudRGB);
+    gicp_alignment.getAlignedCloud(aligned_cloud);
+    EXPECT_TRUE(gicp_alignment.transform_exists_ && gicpb_shim::isValidTransform(gicp_alignment.getFineTransform()));
+    const Matrix4f final_transform = gicp_alignment.getFineTransform() * Matrix4f::Identity();
+    print_tf("pipeline_transform", final_transform);
+    {
+      std::shared_ptr<gicpb_shim::Context> ctx = gicpb_shim::Context::shared();
+      gicpb_shim::transformCloud(*ctx, *source_f, *source_f, final_transform);  // pcl::transformPointCloud in place (:189)
+    }
+    const double voxelize_factor = 3, th = 4e-3 * voxelize_factor;
+    CloudPtr substracted_cloud(new PointCloudRGB);
+    gicpb_shim::removeFromCloud(source_f, target_f, th, substracted_cloud);
+    std::printf("RESULT pipeline_difference %zu\n", substracted_cloud->points.size());
+    int num_of_fods = 0;
+    std::vector<CloudPtr> fods_cloud_array;
+    if (substracted_cloud->points.size() > 1) {  // Utils::isValidCloud
+      FODDetector fod_detector(substracted_cloud, th * 100, 3);
+      fod_detector.clusterPossibleFODs();
+      num_of_fods = fod_detector.fodIndicesToPointCloud(fods_cloud_array);
+    }
+    std::printf("RESULT pipeline_fods %d", num_of_fods);
+    for (const auto& f : fods_cloud_array) std::printf(" %zu", f->points.size());
+    std::printf("\n");
+    // Utils::getNormals on the downsampled CAD cloud (src/Utils.cpp:27-44) through its shim
+    gicpb_shim::NormalCloudT::Ptr normals(new gicpb_shim::NormalCloudT);
+    EXPECT_TRUE(gicpb_shim::getNormals(target_f, 4.0 * leaf_size, normals));
+    size_t finite = 0;
+    double checksum = 0;
+    for (const auto& nrm : normals->points)
+      if (std::isfinite(nrm.normal_x)) {
+        ++finite;
+        checksum += (double)nrm.normal_x + 2.0 * (double)nrm.normal_y + 3.0 * (double)nrm.normal_z + (double)nrm.curvature;
+      }
+    std::printf("RESULT pipeline_normals %zu %.9g %d\n", finite, checksum, (int)normals->is_dense);
+  }
+
   std::printf("RESULT failed %d\n", g_failed);
   return g_failed ? 1 : 0;
 }

@@ -561,6 +561,36 @@ def test_reference_testRunWithCov(cube_pair):
     assert np.allclose(g.getFineTransform(), T1 @ T1, atol=1e-6)  # fine_tf_ is NOT rolled back, as upstream
 
 
+@pytest.mark.parametrize("which", ["cube", "panel", "panel_far_from_origin"])
+def test_normals_match_oracle(engine, oracle, cube_pair, which):
+    """Utils::getNormals (reference src/Utils.cpp:27-44; SURVEY 8f row 2): the NaN pattern is bit-exact; the float moments
+    are added in PCL's order with PCL's roundings, so the normal vectors and curvatures agree with the oracle to the few
+    ulps by which CUDA's atan2f / cosf / sinf differ from glibc's inside pcl::eigen33, amplified by the eigen-gap."""
+    if which == "cube":
+        cloud, radius = cube_pair[0], 0.12
+    else:
+        cloud, radius = synth.panel_points(40000, 9, noise_sigma=5e-4), 0.035
+        if which == "panel_far_from_origin":
+            cloud = (cloud + np.array([30.0, -20.0, 10.0], np.float32)).astype(np.float32)
+        cloud = np.concatenate([cloud, np.array([[50.0, 50.0, 50.0], [np.nan, 1.0, 1.0]], np.float32)])
+    reset(engine)
+    engine.set_target(cloud)
+    nrm, kept = engine.normals(0, radius)
+    ref, rk = oracle.normals(cloud, radius)
+    mask, mk = engine.normal_validity(0, radius)
+    assert kept == rk == mk
+    assert np.array_equal(np.isnan(nrm), np.isnan(ref))
+    assert np.array_equal(np.isfinite(nrm[:, 0]), mask.astype(bool))
+    ok = np.isfinite(ref[:, 0])
+    d = np.abs(nrm[ok, :3] - ref[ok, :3]).max(axis=1)
+    # a flipped sign (n . p within an ulp of 0) or a different choice among equal cross products shows as a big jump: none
+    assert d.max() < 1e-3, d.max()
+    assert np.quantile(d, 0.999) <= 1e-6, np.quantile(d, [0.5, 0.99, 0.999, 1.0])
+    assert (d == 0).mean() > 0.5          # most normals are bit-identical
+    dc = np.abs(nrm[ok, 3] - ref[ok, 3])
+    assert np.quantile(dc, 0.999) <= 1e-6 and dc.max() < 1e-4
+
+
 def test_zero_gate_finds_no_pairs(engine, oracle, cube_pair):
     """setMaxCorrespondenceDistance(int) truncates (include/GICPAlignment.h:138): 0.5 becomes 0.  PCL then tests
     `nn_dists[0] < 0`, finds no pair, throws NotEnoughPointsException inside align() and hasConverged() stays false
