@@ -47,6 +47,8 @@
 #include <sensor_msgs/PointCloud2.h>
 #endif
 
+class GICPAlignment;
+
 namespace gicpb_shim {
 
 // ---- logging (replaces ROS_INFO / ROS_ERROR) -----------------------------------------------------------------------
@@ -153,20 +155,65 @@ inline bool isValidTransform(const Mat4T& tf) {
 // several threads at once need their own (`Context::create()`).
 class Context {
  public:
+  // GICPB_DEVICES=0,1,2,3 (more than one GPU): the registration runs sharded over them inside this process (gicpb_group);
+  // GICPB_DEVICE=n or nothing: one context on that GPU.  get() is always a full single-GPU context (the group's first).
   Context() {
-    int device = 0;
-    if (const char* e = std::getenv("GICPB_DEVICE")) device = std::atoi(e);
+    std::vector<int> devices;
+    if (const char* e = std::getenv("GICPB_DEVICES")) {
+      for (const char* p = e; *p;) {
+        char* end = nullptr;
+        const long d = std::strtol(p, &end, 10);
+        if (end == p) break;
+        devices.push_back((int)d);
+        p = (*end == ',') ? end + 1 : end;
+      }
+    }
+    if (devices.size() > 1) {
+      const int rc = gicpb_group_create(devices.data(), (int)devices.size(), &group_);
+      if (rc != GICPB_OK || !group_)
+        throw std::runtime_error("gicpb_group_create failed (" + std::to_string(rc) + "): GICPB_DEVICES must name B200s");
+      ctx_ = gicpb_group_ctx(group_, 0);
+      return;
+    }
+    int device = devices.empty() ? 0 : devices[0];
+    if (devices.empty())
+      if (const char* e = std::getenv("GICPB_DEVICE")) device = std::atoi(e);
     const int rc = gicpb_create(device, &ctx_);
     if (rc != GICPB_OK || !ctx_)
       throw std::runtime_error("gicpb_create failed (" + std::to_string(rc) + "): libgicp_b200 needs a B200; there is no CPU path");
   }
-  ~Context() { gicpb_destroy(ctx_); }
+  ~Context() {
+    if (group_)
+      gicpb_group_destroy(group_);
+    else
+      gicpb_destroy(ctx_);
+  }
   Context(const Context&) = delete;
   Context& operator=(const Context&) = delete;
   gicpb_ctx* get() const { return ctx_; }
+  bool grouped() const { return group_ != nullptr; }
+  int gpus() const { return group_ ? gicpb_group_size(group_) : 1; }
   void check(int rc, const char* what) const {
     if (rc != GICPB_OK) throw std::runtime_error(std::string(what) + ": " + gicpb_last_error(ctx_));
   }
+  void check_group(int rc, const char* what) const {
+    if (rc != GICPB_OK) throw std::runtime_error(std::string(what) + ": " + gicpb_group_last_error(group_));
+  }
+  // the registration calls: on every GPU of the group, or on the one context
+  void setParams(const gicpb_params& p) {
+    if (group_)
+      check_group(gicpb_group_set_params(group_, &p), "gicpb_group_set_params");
+    else
+      check(gicpb_set_params(ctx_, &p), "gicpb_set_params");
+  }
+  int align(gicpb_align_result* out) { return group_ ? gicpb_group_align(group_, out) : gicpb_align(ctx_, out); }
+  void fitness(const float T[16], double max_range, double* score) {
+    if (group_)
+      check_group(gicpb_group_fitness(group_, T, max_range, score), "gicpb_group_fitness");
+    else
+      check(gicpb_fitness(ctx_, T, max_range, score), "gicpb_fitness");
+  }
+  const char* lastError() const { return group_ ? gicpb_group_last_error(group_) : gicpb_last_error(ctx_); }
   static std::shared_ptr<Context> create() { return std::make_shared<Context>(); }
   // the process-wide context (created on first use, destroyed at exit or by release_shared())
   static std::shared_ptr<Context>& shared_slot() {
@@ -185,6 +232,8 @@ class Context {
 
  private:
   gicpb_ctx* ctx_ = nullptr;
+  gicpb_group* group_ = nullptr;
+  friend class ::GICPAlignment;
 };
 
 inline Context* resolve(Context* given, std::shared_ptr<Context>& hold) {
@@ -398,7 +447,7 @@ class GICPAlignment {
     p.max_iterations = max_iter_;
     p.max_corr_distance = max_corresp_distance_;
     p.transformation_epsilon = tf_epsilon_;
-    ctx_.check(gicpb_set_params(ctx_.get(), &p), "gicpb_set_params");
+    ctx_.setParams(p);
   }
 
   void indexCloud(int which, const CloudPtr& cloud) {
@@ -455,7 +504,13 @@ class GICPAlignment {
   void setInputs(const CloudPtr& target, const CloudPtr& source, bool reuse_indices) {
     if (source->points.empty() || target->points.empty()) throw std::runtime_error("empty cloud");
     if (ctx_.inputs_owner != this) tgt_indexed_ = src_indexed_ = false;
-    if (reuse_indices && (tgt_indexed_ || src_indexed_)) {
+    if (ctx_.grouped()) {
+      // every GPU of the group uploads and indexes the target, and its shard's share of the work on the source
+      ctx_.check_group(gicpb_group_set_clouds(ctx_.group_, &target->points[0].x, (int64_t)target->points.size(),
+                                              (int64_t)sizeof(target->points[0]), &source->points[0].x,
+                                              (int64_t)source->points.size(), (int64_t)sizeof(source->points[0])),
+                       "gicpb_group_set_clouds");
+    } else if (reuse_indices && (tgt_indexed_ || src_indexed_)) {
       // applyCovariances has just indexed these very clouds: index what changed since, then the covariances
       ensureIndexed();
       ctx_.check(gicpb_compute_covariances(ctx_.get()), "gicpb_compute_covariances");
@@ -482,8 +537,9 @@ class GICPAlignment {
 
   // gicp_.align(): solver failures are not errors of the call (PCL swallows them: hasConverged() == false)
   int align() {
-    const int rc = gicpb_align(ctx_.get(), &last_);
-    if (rc == GICPB_E_BADARG || rc == GICPB_E_CUDA || rc == GICPB_E_NCCL || rc == GICPB_E_STATE) ctx_.check(rc, "gicpb_align");
+    const int rc = ctx_.align(&last_);
+    if (rc == GICPB_E_BADARG || rc == GICPB_E_CUDA || rc == GICPB_E_NCCL || rc == GICPB_E_STATE)
+      throw std::runtime_error(std::string("gicpb_align: ") + ctx_.lastError());
     converged_ = last_.converged != 0;
     return rc;
   }
@@ -497,7 +553,7 @@ class GICPAlignment {
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin).count();
     gicpb_shim::log(gicpb_shim::kInfo, "GICP time: %lf s", secs);
     if (converged_) {
-      ctx_.check(gicpb_fitness(ctx_.get(), last_.transform, 1.7976931348623157e308, &fitness_), "gicpb_fitness");
+      ctx_.fitness(last_.transform, 1.7976931348623157e308, &fitness_);
       gicpb_shim::log(gicpb_shim::kInfo, "Converged in %f FitnessScore", fitness_);
       fine_tf_ = gicpb_shim::from_row_major(last_.transform);
       transform_exists_ = gicpb_shim::isValidTransform(fine_tf_);
@@ -521,7 +577,7 @@ class GICPAlignment {
     const Matrix4f temp_tf = gicpb_shim::from_row_major(last_.transform);
     if (converged_) {
       fine_tf_ = temp_tf * fine_tf_;
-      ctx_.check(gicpb_fitness(ctx_.get(), last_.transform, 1.7976931348623157e308, &fitness_), "gicpb_fitness");
+      ctx_.fitness(last_.transform, 1.7976931348623157e308, &fitness_);
       gicpb_shim::log(gicpb_shim::kInfo, "Converged in %f FitnessScore", fitness_);
     } else {
       gicpb_shim::log(gicpb_shim::kError, "GICP no converge");

@@ -112,6 +112,29 @@ int gicpb_peer_export(gicpb_ctx* ctx, unsigned char handle_out[64]);
 int gicpb_peer_import(gicpb_ctx* ctx, const unsigned char* handles, int world);
 int gicpb_peer_disable(gicpb_ctx* ctx); /* back to ncclAllReduce (call on every rank) */
 
+/* ---- one process, several GPUs ----------------------------------------------------------------------------------
+ * The reference's consumer constructs GICPAlignment inside one process (src/LeicaStateMachine.cpp:138-171): a group makes
+ * the sharded path reachable from there, without a launcher.  gicpb_group_create makes one context per entry of
+ * `devices` (SURVEY 8b "create(cfg: device ids, n_gpus)"); every group call below runs the per-context call of the same
+ * name on all of them, one host thread per GPU, the source sharded by rank and the target replicated exactly as with one
+ * process per GPU.  The collectives stay inside the process: target covariances by peer copies, the per-evaluation sum
+ * fused into the cost kernel over peer memory when every pair of devices can map each other (gicpb_group_fused), else
+ * through the host.  No NCCL is needed.  All clouds are HOST clouds.  A group of one device is a plain context.
+ * gicpb_group_ctx(g, 0) is a full context for the single-GPU calls (transform, difference, clusters, ...); do not call
+ * set_* / align / fitness on a member directly while the group is in use. */
+typedef struct gicpb_group gicpb_group;
+int gicpb_group_create(const int* devices, int n_devices, gicpb_group** out);
+void gicpb_group_destroy(gicpb_group* group);
+const char* gicpb_group_last_error(const gicpb_group* group);
+int gicpb_group_size(const gicpb_group* group);
+int gicpb_group_fused(const gicpb_group* group);
+gicpb_ctx* gicpb_group_ctx(gicpb_group* group, int rank);
+int gicpb_group_set_params(gicpb_group* group, const gicpb_params* p);                 /* configParameters :48-54 */
+int gicpb_group_set_clouds(gicpb_group* group, const void* target, int64_t n_target, int64_t target_stride_bytes,
+                           const void* source, int64_t n_source, int64_t source_stride_bytes); /* :89-90 */
+int gicpb_group_align(gicpb_group* group, gicpb_align_result* out);                     /* gicp_.align :96,116 */
+int gicpb_group_fitness(gicpb_group* group, const float transform[16], double max_range, double* score); /* :103,123 */
+
 /* ---- clouds: upload once, index on the GPU (replaces setInputTarget / setInputSource and the two FLANN
  *      kd-tree builds, src/GICPAlignment.cpp:89-90; PCL Registration::initCompute[Reciprocal]) ------- */
 /* Optional hint for HOST clouds: start uploading cloud `which` (0 target, 1 source) on a copy stream now and return

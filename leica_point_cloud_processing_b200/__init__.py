@@ -3,10 +3,10 @@
 
 CUDA (sm_100a) does all the work through libgicp_b200.so; there is no CPU implementation in this package.
 """
-from ._capi import Engine, GicpError, Params, load_library, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
+from ._capi import Engine, EngineGroup, GicpError, Params, load_library, EXPORTED_SYMBOLS, LIB_PATH  # noqa: F401
 from .gicp_alignment import GICPAlignment, remove_from_cloud, is_valid_transform  # noqa: F401
 from .fod_detector import FODDetector, downsample_cloud  # noqa: F401
 
-__all__ = ["Engine", "GicpError", "Params", "GICPAlignment", "remove_from_cloud", "is_valid_transform", "FODDetector",
+__all__ = ["Engine", "EngineGroup", "GicpError", "Params", "GICPAlignment", "remove_from_cloud", "is_valid_transform", "FODDetector",
            "downsample_cloud",
            "load_library", "EXPORTED_SYMBOLS", "LIB_PATH"]

@@ -149,6 +149,17 @@ _SIGNATURES = [
                                                    ctypes.c_int]),
     ("gicpb_pcd_load_xyzrgb", ctypes.c_int, [_VOID_P, ctypes.c_char_p, _VOID_P, ctypes.c_int64, ctypes.c_int,
                                              ctypes.POINTER(PcdInfo)]),
+    ("gicpb_group_create", ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(_VOID_P)]),
+    ("gicpb_group_destroy", None, [_VOID_P]),
+    ("gicpb_group_last_error", ctypes.c_char_p, [_VOID_P]),
+    ("gicpb_group_size", ctypes.c_int, [_VOID_P]),
+    ("gicpb_group_fused", ctypes.c_int, [_VOID_P]),
+    ("gicpb_group_ctx", ctypes.c_void_p, [_VOID_P, ctypes.c_int]),
+    ("gicpb_group_set_params", ctypes.c_int, [_VOID_P, ctypes.POINTER(Params)]),
+    ("gicpb_group_set_clouds", ctypes.c_int, [_VOID_P, _VOID_P, ctypes.c_int64, ctypes.c_int64, _VOID_P, ctypes.c_int64,
+                                              ctypes.c_int64]),
+    ("gicpb_group_align", ctypes.c_int, [_VOID_P, ctypes.POINTER(AlignResult)]),
+    ("gicpb_group_fitness", ctypes.c_int, [_VOID_P, c_float_p, ctypes.c_double, c_double_p]),
     ("gicpb_launch_count", ctypes.c_int64, [_VOID_P]),
     ("gicpb_stream", ctypes.c_void_p, [_VOID_P]),
     ("gicpb_last_far_queries", ctypes.c_int64, [_VOID_P]),
@@ -234,8 +245,13 @@ def _T(T):
 class Engine:
     """Thin object wrapper over one gicpb_ctx."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, _borrowed=None):
         self.lib = load_library()
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a member context of an EngineGroup: the group owns it
+            self.h = _VOID_P(_borrowed)
+            self.device = device
+            return
         h = _VOID_P()
         rc = self.lib.gicpb_create(int(device), ctypes.byref(h))
         if rc != GICPB_OK:
@@ -245,7 +261,8 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.gicpb_destroy(self.h)
+            if self._owned:
+                self.lib.gicpb_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -295,6 +312,17 @@ class Engine:
 
     def peer_disable(self):
         self._check(self.lib.gicpb_peer_disable(self.h))
+
+    def comm_rank(self):
+        r, w = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.gicpb_comm_rank(self.h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
+
+    def shard(self):
+        """[lo, hi) of the sorted source points this context owns (csrc/engine.cu update_shard)"""
+        r, w = self.comm_rank()
+        n = self.grid_info(1)["n_indexed"]
+        return n * r // w, n * (r + 1) // w
 
     def comm_init(self, rank, world, unique_id, libnccl=None):
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
@@ -578,3 +606,80 @@ class Engine:
 
     def launch_count(self):
         return int(self.lib.gicpb_launch_count(self.h))
+
+
+class EngineGroup:
+    """One process, several GPUs (gicpb_group): the source sharded over the devices, the target replicated, one host thread
+    per GPU inside the library.  `devices` may name one GPU several times (host-mediated sums then; for tests on one GPU)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = _VOID_P()
+        rc = self.lib.gicpb_group_create(devs, len(devices), ctypes.byref(h))
+        if rc != GICPB_OK:
+            raise GicpError(rc, "gicpb_group_create failed")
+        self.h = h
+        self.devices = list(devices)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gicpb_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != GICPB_OK:
+            raise GicpError(rc, (self.lib.gicpb_group_last_error(self.h) or b"").decode())
+
+    @property
+    def size(self):
+        return int(self.lib.gicpb_group_size(self.h))
+
+    @property
+    def fused(self):
+        return bool(self.lib.gicpb_group_fused(self.h))
+
+    def member(self, rank):
+        """Engine view of one member context (owned by the group)."""
+        p = self.lib.gicpb_group_ctx(self.h, int(rank))
+        if not p:
+            raise IndexError(rank)
+        return Engine(self.devices[rank], _borrowed=p)
+
+    def set_params(self, **kw):
+        p = self.member(0).get_params()
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+        self._check(self.lib.gicpb_group_set_params(self.h, ctypes.byref(p)))
+        return p
+
+    def set_clouds(self, target, source):
+        kt, tptr, tn, tstride, tdev = _as_cloud(target)
+        ks, sptr, sn, sstride, sdev = _as_cloud(source)
+        if tdev or sdev:
+            raise ValueError("EngineGroup.set_clouds takes host clouds")
+        self._check(self.lib.gicpb_group_set_clouds(self.h, tptr, tn, tstride, sptr, sn, sstride))
+
+    def align(self, raise_on_failure=True):
+        res = AlignResult()
+        rc = self.lib.gicpb_group_align(self.h, ctypes.byref(res))
+        if rc != GICPB_OK and (raise_on_failure or rc in (E_BADARG, E_CUDA, E_NCCL, E_STATE)):
+            self._check(rc)
+        out = {k: getattr(res, k) for k, _ in AlignResult._fields_ if k != "transform"}
+        out["transform"] = np.array(res.transform, np.float32).reshape(4, 4)
+        out["rc"] = rc
+        return out
+
+    def fitness(self, T, max_range=float(np.finfo(np.float64).max)):
+        Tk, Tp = _T(T)
+        s = ctypes.c_double()
+        self._check(self.lib.gicpb_group_fitness(self.h, Tp, max_range, ctypes.byref(s)))
+        return s.value

@@ -14,7 +14,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "../../include/gicp_b200.h"
 #include "cloud_io.hpp"
@@ -162,6 +165,46 @@ double now_ms() {
 
 }  // namespace
 
+// ---- the contexts of one gicpb_group (one process, several GPUs): what the ranks share ------------------------------------
+struct gicpb_ctx;
+struct GroupAbort : std::runtime_error {
+  GroupAbort() : std::runtime_error("another GPU of the group failed") {}
+};
+struct LocalGroup {
+  int world = 0;
+  std::vector<gicpb_ctx*> members;
+  std::vector<double> slots;  // [world][80]: small sums on their way through the host
+  std::mutex mu;
+  std::condition_variable cv;
+  int waiting = 0;
+  unsigned generation = 0;
+  bool failed = false;
+  // every rank's thread arrives; throws on all of them once one rank has failed (so nobody waits for ever)
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (failed) throw GroupAbort();
+    const unsigned gen = generation;
+    if (++waiting == world) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+      return;
+    }
+    cv.wait(lk, [&] { return generation != gen || failed; });
+    if (generation == gen) throw GroupAbort();
+  }
+  void fail() {
+    std::lock_guard<std::mutex> lk(mu);
+    failed = true;
+    cv.notify_all();
+  }
+  void reset() {
+    std::lock_guard<std::mutex> lk(mu);
+    failed = false;
+    waiting = 0;
+  }
+};
+
 // ---- context ------------------------------------------------------------------------------------------------
 struct gicpb_ctx {
   int device = 0;
@@ -226,6 +269,8 @@ struct gicpb_ctx {
   NcclApi* nccl = nullptr;
   NcclApi::comm_t comm = nullptr;
   int rank = 0, world = 1;
+  LocalGroup* local = nullptr;  // member of a gicpb_group: the collectives go over peer copies / the host, not NCCL
+  bool peer_ipc = false;        // peer.peers[] are cudaIpc mappings (closed on destroy)
   // fused cost + cross-GPU sum over peer memory (kernels.hpp PeerReduce); falls back to ncclAllReduce when not set up
   PeerSlots* peer_own = nullptr;
   PeerReduce peer{};
@@ -270,6 +315,9 @@ int guarded(gicpb_ctx* ctx, F&& fn) {
   } catch (const AlignStop& e) {
     ctx->err = e.what();
     return e.code;
+  } catch (const GroupAbort& e) {
+    ctx->err = e.what();
+    return GICPB_E_STATE;
   } catch (const std::exception& e) {
     ctx->err = e.what();
     return GICPB_E_CUDA;
@@ -280,8 +328,30 @@ void check_nccl(gicpb_ctx* c, int rc, const char* what) {
   if (rc != 0) throw NcclError(std::string(what) + ": " + c->nccl->GetErrorString(rc));
 }
 
+// in-process group: `count` (<= 80) doubles of every rank through the host, added in rank order on every rank (identical sums)
+void local_all_reduce(gicpb_ctx* c, double* dev, int count) {
+  LocalGroup* lg = c->local;
+  double* mine = lg->slots.data() + 80 * (size_t)c->rank;
+  GICPB_CUDA(cudaMemcpyAsync(mine, dev, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  lg->barrier();
+  double sum[80];
+  for (int k = 0; k < count; ++k) {
+    double v = 0.0;
+    for (int r = 0; r < lg->world; ++r) v += lg->slots[80 * (size_t)r + k];
+    sum[k] = v;
+  }
+  lg->barrier();  // everybody has read the slots: they may be written again
+  GICPB_CUDA(cudaMemcpyAsync(dev, sum, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  GICPB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
 void all_reduce_sum(gicpb_ctx* c, double* dev, int count) {
   if (c->world <= 1) return;
+  if (c->local) {
+    local_all_reduce(c, dev, count);
+    return;
+  }
   check_nccl(c, c->nccl->AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, c->comm, c->stream), "ncclAllReduce");
 }
 
@@ -327,11 +397,23 @@ void finish_covariances(gicpb_ctx* c) {
   const int chunk = target_chunk(c);
   c->n_src.reserve(3 * (size_t)std::max(ns, 1));
   const FarWork fw = far_work(c, std::max(chunk, ns));
-  if (c->world > 1)
+  if (c->world > 1 && c->local) {
+    // in-process group: every rank's chunk is complete and its buffer in place, then the other chunks come over NVLink
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->local->barrier();
+    for (int r = 0; r < c->world; ++r) {
+      if (r == c->rank) continue;
+      const gicpb_ctx* o = c->local->members[(size_t)r];
+      GICPB_CUDA(cudaMemcpyPeerAsync(c->n_tgt.get() + 3 * (size_t)r * chunk, c->device, o->n_tgt.get() + 3 * (size_t)r * chunk,
+                                     o->device, 3 * (size_t)chunk * sizeof(double), c->stream));
+    }
+  } else if (c->world > 1) {
     check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
                                      kNcclFloat64, c->comm, c->stream), "ncclAllGather");
+  }
   launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream);
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->world > 1 && c->local) c->local->barrier();  // nobody touches its n_tgt again before every copy out of it is done
   c->cov_ready = true;
   c->pairs_valid = false;
 }
@@ -781,6 +863,55 @@ int64_t compute_normals(gicpb_ctx* c, int which, double radius, int64_t* total_p
 
 }  // namespace
 
+// ---- one process, several GPUs (include/gicp_b200.h "gicpb_group") ------------------------------------------------------
+// The reference's consumer builds its GICPAlignment inside ONE process (reference src/LeicaStateMachine.cpp:138-171), so the
+// multi-GPU path must be reachable without a launcher: a group owns one context per device, every group call runs the same
+// per-rank call on all of them from one host thread per GPU (exactly what the ranks of a torchrun job do, optimisers in lock
+// step), and the collectives stay inside the process: target covariances by peer copies, the 14 cost sums fused into the cost
+// kernel over peer memory (kernels.hpp PeerReduce) when every pair of devices can map each other, else through the host.
+struct gicpb_group {
+  LocalGroup lg;
+  std::vector<gicpb_ctx*> ctx;
+  std::string err;
+  bool fused = false;
+};
+
+namespace {
+
+template <typename F>
+int group_run(gicpb_group* g, F fn) {  // fn(rank, ctx) -> status, on one thread per GPU; the first failure is reported
+  const int n = (int)g->ctx.size();
+  std::vector<int> rc((size_t)n, GICPB_OK);
+  g->lg.reset();
+  auto body = [&](int r) {
+    rc[(size_t)r] = fn(r, g->ctx[(size_t)r]);
+    if (rc[(size_t)r] != GICPB_OK) g->lg.fail();  // the others must not wait for this rank at a barrier
+  };
+  std::vector<std::thread> th;
+  for (int r = 1; r < n; ++r) th.emplace_back(body, r);
+  body(0);
+  for (auto& t : th) t.join();
+  int first = GICPB_OK;
+  for (int r = 0; r < n; ++r) {
+    // a rank that only gave up because another one failed is not the cause
+    const bool abort_only = rc[(size_t)r] == GICPB_E_STATE && g->ctx[(size_t)r]->err == GroupAbort().what();
+    if (rc[(size_t)r] != GICPB_OK && !abort_only && first == GICPB_OK) {
+      first = rc[(size_t)r];
+      g->err = "GPU " + std::to_string(g->ctx[(size_t)r]->device) + " (rank " + std::to_string(r) + "): " + g->ctx[(size_t)r]->err;
+    }
+  }
+  if (first == GICPB_OK)
+    for (int r = 0; r < n; ++r)
+      if (rc[(size_t)r] != GICPB_OK) {
+        first = rc[(size_t)r];
+        g->err = g->ctx[(size_t)r]->err;
+        break;
+      }
+  return first;
+}
+
+}  // namespace
+
 // ---- C ABI ---------------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -817,7 +948,13 @@ int gicpb_create(int device, gicpb_ctx** out) {
     if (prop.major < 10) throw CudaError("libgicp_b200 is built for sm_100a only; found sm_" +
                                          std::to_string(prop.major) + std::to_string(prop.minor));
     c->num_sms = prop.multiProcessorCount;
-    if (prop.persistingL2CacheMaxSize > 0 &&
+    // A persisting L2 carve-out for the Mahalanobis array is opt-in (GICPB_L2_PERSIST=1): reserved for the lifetime of the
+    // context it takes 79 of the 126 MB away from everything else - reorder_kernel of an 8 M-point index build ran 0.97 ms
+    // with it and 0.35 ms without - while the evaluations, which keep a quarter of the pairs in shared memory, gain nothing
+    // measurable from it (align 38.57 vs 38.43 ms at 8 M, 2.994 vs 2.996 ms at 1 M).
+    const char* l2env = std::getenv("GICPB_L2_PERSIST");
+    const bool l2_wanted = l2env && *l2env == '1';
+    if (l2_wanted && prop.persistingL2CacheMaxSize > 0 &&
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
       c->l2_persist_bytes = (size_t)prop.persistingL2CacheMaxSize;
       c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
@@ -876,7 +1013,7 @@ void gicpb_destroy(gicpb_ctx* c) {
   if (c->h_sums) cudaFreeHost(c->h_sums);
   if (c->h_cmd) cudaFreeHost(c->h_cmd);
   if (c->h_mom) cudaFreeHost(c->h_mom);
-  if (c->peer.world > 1)
+  if (c->peer.world > 1 && c->peer_ipc)
     for (int r = 0; r < c->peer.world; ++r)
       if (r != c->rank && c->peer.peers[r]) cudaIpcCloseMemHandle(c->peer.peers[r]);
   if (c->peer_own) cudaFree(c->peer_own);
@@ -985,6 +1122,7 @@ int gicpb_peer_import(gicpb_ctx* c, const unsigned char* handles, int world) {
     c->peer.rank = c->rank;
     c->peer.world = world;
     c->peer.seq = 0u;
+    c->peer_ipc = true;
     {
       const char* env = std::getenv("GICPB_PEER_TIMEOUT_MS");
       const double ms = env && *env ? std::atof(env) : 30000.0;
@@ -1673,6 +1811,144 @@ int64_t gicpb_last_far_queries(gicpb_ctx* c) {
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
   if (cudaMemcpy(v, c->far_counter.get(), sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (int64_t)v[1];
+}
+
+
+int gicpb_group_create(const int* devices, int n_devices, gicpb_group** out) {
+  if (!out) return GICPB_E_BADARG;
+  *out = nullptr;
+  if (!devices || n_devices < 1 || n_devices > kMaxPeers) return GICPB_E_BADARG;
+  std::unique_ptr<gicpb_group> g(new gicpb_group);
+  auto cleanup = [&] {
+    for (gicpb_ctx* c : g->ctx) gicpb_destroy(c);
+  };
+  for (int r = 0; r < n_devices; ++r) {
+    gicpb_ctx* c = nullptr;
+    const int rc = gicpb_create(devices[r], &c);
+    if (rc != GICPB_OK) {
+      cleanup();
+      return rc;
+    }
+    g->ctx.push_back(c);
+  }
+  if (n_devices == 1) {
+    *out = g.release();
+    return GICPB_OK;
+  }
+  g->lg.world = n_devices;
+  g->lg.members = g->ctx;
+  g->lg.slots.assign(80 * (size_t)n_devices, 0.0);
+  // The fused sum makes each rank's cost kernel wait for the other ranks' kernels: only sound when every rank has a GPU of
+  // its own (two such kernels on one GPU may never run at the same time) and every pair can map each other's memory.
+  bool fused = true;
+  for (int a = 0; a < n_devices && fused; ++a)
+    for (int b = 0; b < n_devices && fused; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      if (devices[a] == devices[b] || cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can) fused = false;
+    }
+  if (const char* env = std::getenv("GICPB_NO_PEER"))
+    if (*env == '1') fused = false;
+  try {
+    for (int r = 0; r < n_devices; ++r) {
+      gicpb_ctx* c = g->ctx[(size_t)r];
+      DeviceGuard guard(c->device);
+      c->rank = r;
+      c->world = n_devices;
+      c->local = &g->lg;
+      if (!fused) continue;
+      for (int b = 0; b < n_devices; ++b) {
+        if (b == r) continue;
+        const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) GICPB_CUDA(e);
+        (void)cudaGetLastError();
+      }
+      GICPB_CUDA(cudaMalloc(&c->peer_own, sizeof(PeerSlots)));
+      GICPB_CUDA(cudaMemset(c->peer_own, 0, sizeof(PeerSlots)));
+    }
+    if (fused) {
+      const char* env = std::getenv("GICPB_PEER_TIMEOUT_MS");
+      const double ms = env && *env ? std::atof(env) : 30000.0;
+      for (int r = 0; r < n_devices; ++r) {
+        gicpb_ctx* c = g->ctx[(size_t)r];
+        for (int b = 0; b < n_devices; ++b) c->peer.peers[b] = g->ctx[(size_t)b]->peer_own;  // plain device pointers (UVA)
+        c->peer.rank = r;
+        c->peer.world = n_devices;
+        c->peer.seq = 0u;
+        c->peer.timeout_ns = (unsigned long long)(std::max(ms, 1.0) * 1e6);
+        c->peer_ipc = false;
+        c->peer_ready = true;
+      }
+    }
+  } catch (const std::exception&) {
+    cleanup();
+    return GICPB_E_CUDA;
+  }
+  g->fused = fused;
+  *out = g.release();
+  return GICPB_OK;
+}
+
+void gicpb_group_destroy(gicpb_group* g) {
+  if (!g) return;
+  for (gicpb_ctx* c : g->ctx) gicpb_destroy(c);
+  delete g;
+}
+
+const char* gicpb_group_last_error(const gicpb_group* g) { return g ? g->err.c_str() : "null group"; }
+int gicpb_group_size(const gicpb_group* g) { return g ? (int)g->ctx.size() : 0; }
+int gicpb_group_fused(const gicpb_group* g) { return g && g->fused ? 1 : 0; }
+gicpb_ctx* gicpb_group_ctx(gicpb_group* g, int rank) {
+  return (g && rank >= 0 && rank < (int)g->ctx.size()) ? g->ctx[(size_t)rank] : nullptr;
+}
+
+int gicpb_group_set_params(gicpb_group* g, const gicpb_params* p) {
+  if (!g) return GICPB_E_BADARG;
+  for (gicpb_ctx* c : g->ctx) {
+    const int rc = gicpb_set_params(c, p);
+    if (rc != GICPB_OK) {
+      g->err = c->err;
+      return rc;
+    }
+  }
+  return GICPB_OK;
+}
+
+int gicpb_group_set_clouds(gicpb_group* g, const void* target, int64_t n_target, int64_t target_stride, const void* source,
+                           int64_t n_source, int64_t source_stride) {
+  if (!g) return GICPB_E_BADARG;
+  return group_run(g, [&](int, gicpb_ctx* c) {
+    // host clouds: both uploads start on the copy stream (the source's runs beside the target's index build)
+    int rc = gicpb_prefetch_cloud(c, 0, target, n_target, target_stride);
+    if (rc == GICPB_OK) rc = gicpb_prefetch_cloud(c, 1, source, n_source, source_stride);
+    if (rc == GICPB_OK) rc = gicpb_set_clouds(c, target, n_target, target_stride, source, n_source, source_stride, 0);
+    return rc;
+  });
+}
+
+int gicpb_group_align(gicpb_group* g, gicpb_align_result* out) {
+  if (!g || !out) return GICPB_E_BADARG;
+  std::vector<gicpb_align_result> res(g->ctx.size());
+  const int rc = group_run(g, [&](int r, gicpb_ctx* c) { return gicpb_align(c, &res[(size_t)r]); });
+  *out = res[0];
+  // whole-job accounting: the ranks searched disjoint shards of the same passes
+  for (size_t r = 1; r < res.size(); ++r) {
+    out->corr_far_queries += res[r].corr_far_queries;
+    out->ms_corr = std::max(out->ms_corr, res[r].ms_corr);
+    if (rc == GICPB_OK && std::memcmp(res[r].transform, res[0].transform, sizeof(res[0].transform)) != 0) {
+      g->err = "the GPUs of the group disagree on the transform";
+      return GICPB_E_STATE;
+    }
+  }
+  return rc;
+}
+
+int gicpb_group_fitness(gicpb_group* g, const float transform[16], double max_range, double* score) {
+  if (!g || !score) return GICPB_E_BADARG;
+  std::vector<double> sc(g->ctx.size(), 0.0);
+  const int rc = group_run(g, [&](int r, gicpb_ctx* c) { return gicpb_fitness(c, transform, max_range, &sc[(size_t)r]); });
+  *score = sc[0];
+  return rc;
 }
 
 }  // extern "C"

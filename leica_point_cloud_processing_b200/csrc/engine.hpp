@@ -65,6 +65,23 @@ class DevBuf {
   size_t cap_ = 0;
 };
 
+// Stable LSD radix sort of (key, value) pairs, one kernel per 8-bit digit (sort_scan.cu "onesweep").  prepare() zeroes the
+// digit histograms; the producer of the keys may count them itself into hist() ([pass][256], digit = (key >> 8 pass) & 255)
+// and pass hist_ready = true.  sort() returns true if the result is in the *_b buffers.
+class RadixSorter {
+ public:
+  void prepare(int64_t n, cudaStream_t stream);
+  uint32_t* hist() const { return work_.get(); }
+  bool sort(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, int64_t n, int key_bits, bool hist_ready,
+            cudaStream_t stream);
+
+ private:
+  static constexpr size_t kWorkWords = 1024 + 8;  // 4 x 256 digit counts, 4 tile cursors
+  DevBuf<uint32_t> work_;
+  DevBuf<unsigned long long> status_;  // [tile][digit]: (epoch << 2 | kind) << 32 | count
+  uint32_t epoch_ = 0;
+};
+
 // Per-cloud spatial index (see common.cuh).  build() runs the whole pipeline on `stream`:
 // ingest (strided xyz -> float4 + bbox) -> density probe -> cell keys -> radix sort -> reorder -> brick/cell tables.
 class GridIndex {
@@ -74,6 +91,7 @@ class GridIndex {
   GridIndex& operator=(const GridIndex&) = delete;
   ~GridIndex() {
     if (h_pin_) cudaFreeHost(h_pin_);
+    if (ev_slots_) cudaEventDestroy(ev_slots_);
   }
   struct Info {
     int64_t n_points = 0, n_indexed = 0;
@@ -106,7 +124,10 @@ class GridIndex {
   Info info_{};
   DevBuf<unsigned char> raw_;
   DevBuf<float4> pts_unsorted_, pts_sorted_;
-  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, hist_, scan_tmp_;
+  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, scan_tmp_;
+  DevBuf<uint32_t> occ_, brick_rank_, brick_first_;  // brick occupancy marks, their ranks; first sorted point of every slot
+  RadixSorter sorter_;
+  cudaEvent_t ev_slots_ = nullptr;
   DevBuf<uint32_t> occ_bits_;
   DevBuf<int> brick_slot_;
   DevBuf<uint32_t> cell_start_;

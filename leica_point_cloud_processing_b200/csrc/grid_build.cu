@@ -14,7 +14,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+#include <vector>
 
 #include "engine.hpp"
 
@@ -138,22 +141,32 @@ __global__ void __launch_bounds__(256) popcount_kernel(const unsigned* __restric
   if (c) atomicAdd(&out[l], c);
 }
 
-__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ pts, int64_t n, GridView g,
-                                                    uint32_t sentinel, uint32_t* __restrict__ keys,
-                                                    uint32_t* __restrict__ vals) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
-  uint32_t key = sentinel;
-  if (finite3(p.x, p.y, p.z)) {
-    const int cx = clampi(cell_of(p.x, g.ox, g.inv_h), 0, g.nx - 1);
-    const int cy = clampi(cell_of(p.y, g.oy, g.inv_h), 0, g.ny - 1);
-    const int cz = clampi(cell_of(p.z, g.oz, g.inv_h), 0, g.nz - 1);
-    const uint32_t b = (uint32_t)brick_index(g, cx >> kBrickShift, cy >> kBrickShift, cz >> kBrickShift);
-    key = b * kBrickCells + local_code(cx & 7, cy & 7, cz & 7);
+// key of every point, the occupancy mark of its brick and the digit histograms of all radix passes (RadixSorter::hist):
+// one read of the points feeds the sort and the brick table
+__global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ pts, int64_t n, GridView g, uint32_t sentinel,
+                                                    int passes, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                    uint32_t* __restrict__ occ, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[4][256];
+  for (int i = threadIdx.x; i < 4 * 256; i += 256) (&h[0][0])[i] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float4 p = pts[i];
+    uint32_t key = sentinel;
+    if (finite3(p.x, p.y, p.z)) {
+      const int cx = clampi(cell_of(p.x, g.ox, g.inv_h), 0, g.nx - 1);
+      const int cy = clampi(cell_of(p.y, g.oy, g.inv_h), 0, g.ny - 1);
+      const int cz = clampi(cell_of(p.z, g.oz, g.inv_h), 0, g.nz - 1);
+      const uint32_t b = (uint32_t)brick_index(g, cx >> kBrickShift, cy >> kBrickShift, cz >> kBrickShift);
+      key = b * kBrickCells + local_code(cx & 7, cy & 7, cz & 7);
+      occ[b] = 1u;
+    }
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    for (int p8 = 0; p8 < passes; ++p8) atomicAdd(&h[p8][(key >> (8 * p8)) & 255u], 1u);
   }
-  keys[i] = key;
-  vals[i] = (uint32_t)i;
+  __syncthreads();
+  for (int p8 = 0; p8 < passes; ++p8)
+    if (h[p8][threadIdx.x]) atomicAdd(&hist[p8 * 256 + threadIdx.x], h[p8][threadIdx.x]);
 }
 
 // gather the points into sorted order and record the inverse permutation (original index -> sorted position;
@@ -172,29 +185,23 @@ __global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__
   }
 }
 
-// flags[i] = 1 iff sorted point i is the first point of its brick
-__global__ void __launch_bounds__(256) brick_flags_kernel(const uint32_t* __restrict__ keys, int n_valid,
-                                                           uint32_t* __restrict__ flags) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
-  flags[i] = (i == 0 || (keys[i - 1] >> 9) != (keys[i] >> 9)) ? 1u : 0u;
-}
-
-// brick heads: slot = rank of the brick among the occupied bricks (so slots ascend with the brick index); set the
-// brick's bit in its superbrick mask and the superbrick's bit in its hyperbrick mask
-__global__ void __launch_bounds__(256) brick_slots_kernel(const uint32_t* __restrict__ keys,
-                                                           const uint32_t* __restrict__ flags,
-                                                           const uint32_t* __restrict__ ranks, int n_valid, GridView g,
-                                                           int* __restrict__ brick_slot,
+// brick table from the occupancy marks (rank = exclusive scan of occ): slot = rank of the brick among the occupied bricks
+// (so slots ascend with the brick index), -1 for an empty brick; the brick's bit in its superbrick mask and the
+// superbrick's bit in its hyperbrick mask; scratch[7] = number of occupied bricks
+__global__ void __launch_bounds__(256) brick_table_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ rank,
+                                                           int n_bricks, GridView g, int* __restrict__ brick_slot,
                                                            unsigned long long* __restrict__ sb_mask,
                                                            unsigned long long* __restrict__ hb_mask,
                                                            unsigned* __restrict__ scratch) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_valid) return;
-  if (i == n_valid - 1) scratch[7] = ranks[i] + flags[i];  // number of occupied bricks
-  if (!flags[i]) return;
-  const int b = (int)(keys[i] >> 9);
-  brick_slot[b] = (int)ranks[i];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bricks) return;
+  const uint32_t o = occ[b], r = rank[b];
+  if (b == n_bricks - 1) scratch[7] = r + o;
+  if (!o) {
+    brick_slot[b] = -1;
+    return;
+  }
+  brick_slot[b] = (int)r;
   const int bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
   const int sx = bx >> 2, sy = by >> 2, sz = bz >> 2;
   atomicOr(&sb_mask[((size_t)sz * g.nsy + sy) * g.nsx + sx], 1ull << (((bz & 3) << 4) | ((by & 3) << 2) | (bx & 3)));
@@ -202,42 +209,96 @@ __global__ void __launch_bounds__(256) brick_slots_kernel(const uint32_t* __rest
            1ull << (((sz & 3) << 4) | ((sy & 3) << 2) | (sx & 3)));
 }
 
-// cell_start: every entry (slot, code) = index of the first sorted point whose (slot, code) is >= it.  Point i
-// writes the entries between its predecessor's cell (exclusive) and its own cell (inclusive); the last point also
-// closes its brick and writes the terminating entry.  Each entry is written exactly once.
-__global__ void __launch_bounds__(256) cell_start_kernel(const uint32_t* __restrict__ keys,
-                                                          const uint32_t* __restrict__ flags,
-                                                          const uint32_t* __restrict__ ranks, int n_valid,
-                                                          uint32_t* __restrict__ cell_start,
-                                                          unsigned* __restrict__ scratch) {
+// cell_start in two steps.  Heads: the first sorted point of every occupied cell writes its index into the cell's entry
+// (all other entries hold 0xffffffff) and the first point of every brick into brick_first[slot].  Fill: one warp per
+// brick turns its 512 entries into "index of the first sorted point whose (slot, code) is >= this one" = the minimum of
+// the head entries at or after it, or the first point of the next brick (a suffix minimum: head indices ascend with the
+// code).  The last brick also writes the terminating entry.
+__global__ void __launch_bounds__(256) cell_heads_kernel(const uint32_t* __restrict__ keys, int n_valid,
+                                                          const int* __restrict__ brick_slot, uint32_t* __restrict__ cell_start,
+                                                          uint32_t* __restrict__ brick_first, unsigned* __restrict__ scratch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool head = false;
   if (i < n_valid) {
     const uint32_t k = keys[i];
-    const uint32_t c = k & 511u;
-    const uint32_t slot = ranks[i] + flags[i] - 1u;
-    uint32_t* cs = cell_start + (size_t)slot * kBrickCells;
-    if (i == 0) {
-      for (uint32_t code = 0; code <= c; ++code) cs[code] = 0u;
-      head = true;
-    } else {
-      const uint32_t kp = keys[i - 1];
-      head = kp != k;
-      if (!flags[i]) {
-        for (uint32_t code = (kp & 511u) + 1u; code <= c; ++code) cs[code] = (uint32_t)i;
-      } else {
-        uint32_t* csp = cs - kBrickCells;  // the previous point lives in the previous slot
-        for (uint32_t code = (kp & 511u) + 1u; code < (uint32_t)kBrickCells; ++code) csp[code] = (uint32_t)i;
-        for (uint32_t code = 0; code <= c; ++code) cs[code] = (uint32_t)i;
-      }
-    }
-    if (i == n_valid - 1) {
-      for (uint32_t code = c + 1u; code <= (uint32_t)kBrickCells; ++code) cs[code] = (uint32_t)n_valid;
+    const uint32_t kp = i > 0 ? keys[i - 1] : ~k;
+    head = kp != k;
+    if (head) {
+      const int slot = brick_slot[k >> 9];
+      cell_start[(size_t)slot * kBrickCells + (k & 511u)] = (uint32_t)i;
+      if (i == 0 || (kp >> 9) != (k >> 9)) brick_first[slot] = (uint32_t)i;
     }
   }
   const unsigned heads = __popc(__ballot_sync(kFullMask, head));
   if ((threadIdx.x & 31) == 0 && heads) atomicAdd(&scratch[8], heads);  // occupied cells (statistics only)
 }
+
+__global__ void __launch_bounds__(128) cell_fill_kernel(uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ brick_first,
+                                                         int n_slots, int n_valid) {
+  const int slot = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (slot >= n_slots) return;
+  const uint32_t carry = slot + 1 < n_slots ? brick_first[slot + 1] : (uint32_t)n_valid;
+  uint4* cs = reinterpret_cast<uint4*>(cell_start + (size_t)slot * kBrickCells) + 4 * lane;  // entries [16 lane, 16 lane + 16)
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = cs[k];
+  uint32_t lm = 0xffffffffu;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) lm = min(lm, min(min(v[k].x, v[k].y), min(v[k].z, v[k].w)));
+  uint32_t incl = lm;  // minimum over the lanes >= this one
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_down_sync(kFullMask, incl, o);
+    if (lane + o < 32) incl = min(incl, t);
+  }
+  uint32_t run = __shfl_down_sync(kFullMask, incl, 1);
+  run = lane == 31 ? carry : min(run, carry);
+#pragma unroll
+  for (int k = 3; k >= 0; --k) {
+    run = min(run, v[k].w); v[k].w = run;
+    run = min(run, v[k].z); v[k].z = run;
+    run = min(run, v[k].y); v[k].y = run;
+    run = min(run, v[k].x); v[k].x = run;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cs[k] = v[k];
+  if (slot == n_slots - 1 && lane == 0) cell_start[(size_t)n_slots * kBrickCells] = (uint32_t)n_valid;
+}
+
+// GICPB_BUILD_TRACE=1: CUDA-event time of every phase of a build, printed to stderr (measurement aid, off by default)
+struct BuildTrace {
+  bool on;
+  cudaStream_t stream;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  explicit BuildTrace(cudaStream_t s) : stream(s) {
+    static const bool enabled = [] {
+      const char* e = std::getenv("GICPB_BUILD_TRACE");
+      return e && *e && *e != '0';
+    }();
+    on = enabled;
+  }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    marks.emplace_back(name, e);
+  }
+  void report(int64_t n, double wall_ms) {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    std::string line = "[gicpb build trace] n " + std::to_string(n) + " wall " + std::to_string(wall_ms) + " ms:";
+    for (size_t i = 1; i < marks.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      char buf[96];
+      std::snprintf(buf, sizeof(buf), " %s %.3f", marks[i].first, ms);
+      line += buf;
+    }
+    std::fprintf(stderr, "%s\n", line.c_str());
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+};
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -332,9 +393,9 @@ void prefer_shared_carveout_grid() {
   cudaFuncSetAttribute(popcount_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(keys_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(brick_flags_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(brick_slots_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-  cudaFuncSetAttribute(cell_start_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(brick_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(cell_heads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(cell_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(brick_plane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   (void)cudaGetLastError();
 }
@@ -342,6 +403,8 @@ void prefer_shared_carveout_grid() {
 void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
                       float points_per_cell, cudaStream_t stream, HostStager* stager) {
   const auto t_begin = std::chrono::steady_clock::now();
+  BuildTrace trace(stream);
+  trace.mark("begin");
   ready_ = false;
   if (n <= 0) throw ArgError("cloud is empty");
   if (n > 0x7fffff00LL) throw ArgError("cloud has more than 2^31 points");
@@ -362,6 +425,7 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
     }
     d_raw = raw_.get();
   }
+  trace.mark("upload");
   pts_unsorted_.reserve(n);
   pts_sorted_.reserve(n);
   scratch_.reserve(64);
@@ -374,6 +438,7 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   unsigned* occ = h_pin_ + 16;            // kProbeLevels words of the density probe
   constexpr size_t kHsBytes = 16 * sizeof(unsigned);
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
+  trace.mark("ingest");
   GICPB_CUDA(cudaStreamSynchronize(stream));
   const int64_t n_valid = hs[6];
   info_.n_indexed = n_valid;
@@ -469,29 +534,6 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   g.nbz = bd[2];
   g.n = (int)n_valid;
 
-  // ---- keys + sort + reorder --------------------------------------------------------------------------
-  keys_a_.reserve(n);
-  keys_b_.reserve(n);
-  vals_a_.reserve(n);
-  vals_b_.reserve(n);
-  hist_.reserve(radix_sort_hist_entries(n));
-  scan_tmp_.reserve(scan_tmp_entries(std::max<int64_t>((int64_t)radix_sort_hist_entries(n), n)));
-  const uint32_t sentinel = (uint32_t)(n_bricks * kBrickCells);
-  int key_bits = 1;
-  while ((1ull << key_bits) <= (unsigned long long)sentinel) ++key_bits;
-  keys_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, g, sentinel, keys_a_.get(),
-                                                      vals_a_.get());
-  GICPB_LAUNCHED();
-  const bool in_b = radix_sort_pairs(keys_a_.get(), vals_a_.get(), keys_b_.get(), vals_b_.get(), hist_.get(),
-                                     scan_tmp_.get(), n, key_bits, stream);
-  const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
-  const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
-  pos_of_.reserve(n);
-  reorder_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, n, pts_sorted_.get(),
-                                                         pos_of_.get());
-  GICPB_LAUNCHED();
-
-  // ---- brick / cell tables ----------------------------------------------------------------------------
   g.nsx = (bd[0] + 3) / 4;
   g.nsy = (bd[1] + 3) / 4;
   g.nsz = (bd[2] + 3) / 4;
@@ -499,32 +541,68 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   g.nhy = (g.nsy + 3) / 4;
   g.nhz = (g.nsz + 3) / 4;
   const size_t n_sb = (size_t)g.nsx * g.nsy * g.nsz, n_hb = (size_t)g.nhx * g.nhy * g.nhz;
+
+  trace.mark("probe");
+  // ---- keys (+ brick occupancy + digit histograms) -> brick table -> sort -> reorder ------------------------------
+  keys_a_.reserve(n);
+  keys_b_.reserve(n);
+  vals_a_.reserve(n);
+  vals_b_.reserve(n);
+  occ_.reserve(n_bricks);
+  brick_rank_.reserve(n_bricks);
+  scan_tmp_.reserve(scan_tmp_entries(n_bricks));
   brick_slot_.reserve(n_bricks);
   sb_mask_.reserve(n_sb);
   hb_mask_.reserve(n_hb);
-  GICPB_CUDA(cudaMemsetAsync(brick_slot_.get(), 0xff, (size_t)n_bricks * sizeof(int), stream));
+  const uint32_t sentinel = (uint32_t)(n_bricks * kBrickCells);
+  int key_bits = 1;
+  while ((1ull << key_bits) <= (unsigned long long)sentinel) ++key_bits;
+  sorter_.prepare(n, stream);
+  GICPB_CUDA(cudaMemsetAsync(occ_.get(), 0, (size_t)n_bricks * sizeof(uint32_t), stream));
   GICPB_CUDA(cudaMemsetAsync(sb_mask_.get(), 0, n_sb * sizeof(unsigned long long), stream));
   GICPB_CUDA(cudaMemsetAsync(hb_mask_.get(), 0, n_hb * sizeof(unsigned long long), stream));
-  uint32_t* flags = in_b ? keys_a_.get() : keys_b_.get();  // the other key / value buffers are free now
-  uint32_t* ranks = in_b ? vals_a_.get() : vals_b_.get();
-  brick_flags_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, flags);
+  keys_kernel<<<std::min<unsigned>(blocks_for(n, 256 * 4), 148u * 4u), 256, 0, stream>>>(
+      pts_unsorted_.get(), n, g, sentinel, (key_bits + 7) / 8, keys_a_.get(), vals_a_.get(), occ_.get(), sorter_.hist());
   GICPB_LAUNCHED();
-  exclusive_scan_u32(flags, ranks, n_valid, scan_tmp_.get(), stream);
-  brick_slots_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, g,
+  trace.mark("keys");
+  exclusive_scan_u32(occ_.get(), brick_rank_.get(), n_bricks, scan_tmp_.get(), stream);
+  brick_table_kernel<<<blocks_for(n_bricks, 256), 256, 0, stream>>>(occ_.get(), brick_rank_.get(), (int)n_bricks, g,
                                                                     brick_slot_.get(), sb_mask_.get(), hb_mask_.get(),
                                                                     scratch_.get());
   GICPB_LAUNCHED();
+  // the number of occupied bricks is read back while the sort runs
+  if (!ev_slots_) GICPB_CUDA(cudaEventCreateWithFlags(&ev_slots_, cudaEventDisableTiming));
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
-  GICPB_CUDA(cudaStreamSynchronize(stream));
-  const int64_t n_slots = hs[7];
-  cell_start_.reserve((size_t)n_slots * kBrickCells + 1);
-  cell_start_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, flags, ranks, (int)n_valid, cell_start_.get(),
-                                                                   scratch_.get());
+  GICPB_CUDA(cudaEventRecord(ev_slots_, stream));
+  trace.mark("bricks");
+  const bool in_b = sorter_.sort(keys_a_.get(), vals_a_.get(), keys_b_.get(), vals_b_.get(), n, key_bits, true, stream);
+  const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
+  const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
+  trace.mark("sort");
+  pos_of_.reserve(n);
+  reorder_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, n, pts_sorted_.get(),
+                                                         pos_of_.get());
   GICPB_LAUNCHED();
+
+  trace.mark("reorder");
+  // ---- cell table -----------------------------------------------------------------------------------------
+  GICPB_CUDA(cudaEventSynchronize(ev_slots_));
+  const int64_t n_slots = hs[7];
+  cell_start_.reserve((size_t)n_slots * kBrickCells + 4);
+  brick_first_.reserve((size_t)n_slots + 1);
+  GICPB_CUDA(cudaMemsetAsync(cell_start_.get(), 0xff, ((size_t)n_slots * kBrickCells + 1) * sizeof(uint32_t), stream));
+  cell_heads_kernel<<<blocks_for(n_valid, 256), 256, 0, stream>>>(skeys, (int)n_valid, brick_slot_.get(), cell_start_.get(),
+                                                                   brick_first_.get(), scratch_.get());
+  GICPB_LAUNCHED();
+  cell_fill_kernel<<<blocks_for(n_slots * 32, 128), 128, 0, stream>>>(cell_start_.get(), brick_first_.get(), (int)n_slots,
+                                                                      (int)n_valid);
+  GICPB_LAUNCHED();
+  trace.mark("cells");
   brick_plane_.reserve((size_t)n_slots * 5);
   brick_plane_kernel<<<blocks_for(n_slots * 32, 128), 128, 0, stream>>>(pts_sorted_.get(), cell_start_.get(), (int)n_slots,
                                                                         brick_plane_.get());
   GICPB_LAUNCHED();
+  trace.mark("plane");
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
 
@@ -545,6 +623,7 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   info_.ms_build =
       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   ready_ = true;
+  trace.report(n, info_.ms_build);
 }
 
 }  // namespace gicpb

@@ -1,0 +1,122 @@
+// sort_micro.cu - the onesweep radix sort of sort_scan.cu against std::stable_sort and against the three-kernel-per-pass sort
+// it replaces; plus the cost of the two halves of reorder_kernel (gather of float4 rows, scatter of the inverse permutation).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../leica_point_cloud_processing_b200/csrc sort_micro.cu -o sort_micro
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include "sort_scan.cu"
+
+namespace gicpb {
+std::atomic<int64_t> g_launch_count{0};
+}
+using namespace gicpb;
+
+__global__ void gather_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int64_t n, float4* __restrict__ sorted) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sorted[i] = pts[vals[i]];
+}
+__global__ void inverse_kernel(const uint32_t* __restrict__ vals, int64_t n, int* __restrict__ pos_of) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos_of[vals[i]] = (int)i;
+}
+__global__ void both_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals, int64_t n, float4* __restrict__ sorted,
+                            int* __restrict__ pos_of) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t oi = vals[i];
+    sorted[i] = pts[oi];
+    pos_of[oi] = (int)i;
+  }
+}
+
+template <class F>
+float time_ms(F f, int reps, cudaStream_t s) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  f();
+  cudaStreamSynchronize(s);
+  cudaEventRecord(a, s);
+  for (int r = 0; r < reps; ++r) f();
+  cudaEventRecord(b, s);
+  cudaEventSynchronize(b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms / reps;
+}
+
+int main(int argc, char** argv) {
+  const long long only_n = argc > 2 ? std::atoll(argv[1]) : 0;
+  const int only_bits = argc > 2 ? std::atoi(argv[2]) : 0;
+  cudaStream_t s;
+  cudaStreamCreate(&s);
+  std::mt19937 rng(7);
+  int bad = 0;
+  RadixSorter sorter;
+  for (int64_t n : {1LL, 33LL, 4096LL, 4097LL, 100000LL, 1000000LL, 8000000LL}) {
+    for (int bits : {7, 23, 26, 32}) {
+      if (only_n && (n != only_n || bits != only_bits)) continue;
+      std::vector<uint32_t> hk(n), hv(n);
+      const uint32_t mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
+      for (int64_t i = 0; i < n; ++i) {
+        hk[i] = (bits == 26 && (i & 3)) ? (uint32_t)(i / 7) & mask : (uint32_t)rng() & mask;  // 26: long equal runs + random
+        hv[i] = (uint32_t)i;
+      }
+      DevBuf<uint32_t> ka, kb, va, vb, hist, tmp;
+      ka.reserve(n); kb.reserve(n); va.reserve(n); vb.reserve(n);
+      hist.reserve(radix_sort_hist_entries(n));
+      tmp.reserve(scan_tmp_entries(std::max<int64_t>((int64_t)radix_sort_hist_entries(n), n)));
+      auto upload = [&] {
+        cudaMemcpyAsync(ka.get(), hk.data(), n * 4, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(va.get(), hv.data(), n * 4, cudaMemcpyHostToDevice, s);
+      };
+      upload();
+      sorter.prepare(n, s);
+      const bool in_b = sorter.sort(ka.get(), va.get(), kb.get(), vb.get(), n, bits, false, s);
+      std::vector<uint32_t> rk(n), rv(n);
+      cudaMemcpyAsync(rk.data(), in_b ? kb.get() : ka.get(), n * 4, cudaMemcpyDeviceToHost, s);
+      cudaMemcpyAsync(rv.data(), in_b ? vb.get() : va.get(), n * 4, cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) { std::printf("CUDA error %s\n", cudaGetErrorString(cudaGetLastError())); return 2; }
+      std::vector<uint32_t> order(n);
+      std::iota(order.begin(), order.end(), 0u);
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hk[a] < hk[b]; });
+      int64_t wrong = 0;
+      for (int64_t i = 0; i < n; ++i) wrong += (rv[i] != order[i]) || (rk[i] != hk[order[i]]);
+      if (wrong) ++bad;
+      float ms_new = 0, ms_old = 0, ms_match = 0;
+      if (n >= 100000) {
+
+        // timing on already-moved data is fine: same key multiset per pass
+        upload(); cudaStreamSynchronize(s);
+        ms_new = time_ms([&] { sorter.prepare(n, s); sorter.sort(ka.get(), va.get(), kb.get(), vb.get(), n, bits, false, s); }, 10, s);
+        upload(); cudaStreamSynchronize(s);
+        ms_old = time_ms([&] { radix_sort_pairs(ka.get(), va.get(), kb.get(), vb.get(), hist.get(), tmp.get(), n, bits, s); }, 10, s);
+      }
+      std::printf("n %9lld bits %2d: %s (%lld wrong)  onesweep %.3f ms (match_any %.3f)  old %.3f ms\n", (long long)n, bits,
+                  wrong ? "MISMATCH" : "ok", (long long)wrong, ms_new, ms_match, ms_old);
+    }
+  }
+  for (int64_t n : {1000000LL, 8000000LL}) {
+    if (only_n) break;
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::shuffle(perm.begin(), perm.end(), rng);
+    DevBuf<uint32_t> vals;
+    DevBuf<float4> pts, sorted;
+    DevBuf<int> pos;
+    vals.reserve(n); pts.reserve(n); sorted.reserve(n); pos.reserve(n);
+    cudaMemcpy(vals.get(), perm.data(), n * 4, cudaMemcpyHostToDevice);
+    cudaMemset(pts.get(), 0, n * 16);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    const float g = time_ms([&] { gather_kernel<<<nb, 256, 0, s>>>(pts.get(), vals.get(), n, sorted.get()); }, 10, s);
+    const float iv = time_ms([&] { inverse_kernel<<<nb, 256, 0, s>>>(vals.get(), n, pos.get()); }, 10, s);
+    const float bo = time_ms([&] { both_kernel<<<nb, 256, 0, s>>>(pts.get(), vals.get(), n, sorted.get(), pos.get()); }, 10, s);
+    std::printf("reorder n %lld random permutation: gather %.3f ms, inverse scatter %.3f ms, both %.3f ms\n", (long long)n, g, iv, bo);
+  }
+  std::printf("RESULT %s\n", bad ? "FAILED" : "ok");
+  return bad ? 1 : 0;
+}

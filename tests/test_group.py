@@ -1,0 +1,88 @@
+"""gicpb_group: one process, several GPUs behind the C ABI (VERDICT r1 missing #2; SURVEY 8b "create(cfg: device ids,
+n_gpus)").  On a one-GPU box the group is made of two (and three) contexts on the SAME device - the sums then go through
+the host, never through kernels that wait for one another - which exercises the sharding, the in-process gather of the
+target covariances and the lock-step optimisers; on a box with two GPUs the fused peer-memory reduction runs as well.
+The answer must be the oracle's, and the single-context engine's."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cases(oracle):
+    from leica_point_cloud_processing_b200 import synth
+    mesh = json.load(open(os.path.join(ROOT, "tests", "golden", "cube_mesh.json")))
+    src = oracle.sample_mesh(np.array(mesh["vertices"], np.float32), np.array(mesh["faces"], np.int32), 5000)
+    tgt = oracle.transform(oracle.rotation_rpy(0.0, 0.0, 0.175), src)
+    ps, pt, _ = synth.make_pair(60_000, 60_000)
+    return [("cube gate 5", src, tgt, dict(max_corr_distance=5.0, transformation_epsilon=5e-4)),
+            ("cube default gate", src, tgt, dict()),
+            ("panel 60k gate 1", ps, pt, dict(max_corr_distance=1.0))]
+
+
+def _check_group(devices, oracle, engine):
+    from leica_point_cloud_processing_b200 import EngineGroup, synth
+    from oracle.oracle import default_params
+    grp = EngineGroup(devices)
+    try:
+        assert grp.size == len(devices)
+        if len(set(devices)) < len(devices):
+            assert not grp.fused          # ranks sharing a GPU never wait for each other inside a kernel
+        for name, s, t, prm in _cases(oracle):
+            full = {**dict(max_corr_distance=4e-2, transformation_epsilon=4e-3), **prm}
+            grp.set_params(**full)
+            grp.set_clouds(t, s)
+            res = grp.align()
+            fit = grp.fitness(res["transform"])
+            ref = oracle.align(s, t, default_params(**prm))
+            fit_ref = oracle.fitness(s, t, ref["T"])
+            diag = float(np.linalg.norm(t.max(0) - t.min(0)))
+            assert res["converged"] == 1, name
+            assert synth.rotation_error_rad(res["transform"], ref["T"]) <= 1e-4, name
+            assert synth.translation_error(res["transform"], ref["T"]) <= 1e-5 * diag, name
+            assert abs(fit - fit_ref) <= 1e-4 * abs(fit_ref), name
+            assert res["outer_iterations"] == ref["outer_iterations"], name
+            # and the single-context engine on the same clouds
+            engine.set_params(**full)
+            engine.set_clouds(t, s)
+            one = engine.align()
+            assert one["outer_iterations"] == res["outer_iterations"], name
+            assert np.allclose(one["transform"], res["transform"], atol=1e-6), name
+            # every member holds its shard: the shards tile the source
+            n_src = sum(grp.member(r).shard()[1] - grp.member(r).shard()[0] for r in range(grp.size))
+            assert n_src == len(s), name
+    finally:
+        grp.close()
+        engine.set_params(max_corr_distance=4e-2, transformation_epsilon=4e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_group_on_one_gpu_matches_oracle(oracle, engine, n):
+    _check_group([0] * n, oracle, engine)
+
+
+@pytest.mark.gpu
+def test_group_on_two_gpus_matches_oracle(oracle, engine):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _check_group([0, 1], oracle, engine)
+
+
+@pytest.mark.gpu
+def test_group_reports_the_failing_rank(oracle):
+    """an error on the ranks (too few points for k = 20) comes back as the status and message, nothing hangs"""
+    from leica_point_cloud_processing_b200 import EngineGroup, GicpError
+    grp = EngineGroup([0, 0])
+    try:
+        pts = np.random.default_rng(0).random((10, 3)).astype(np.float32)
+        grp.set_clouds(pts, pts)          # indexes; covariances are left to align (k does not fit)
+        with pytest.raises(GicpError) as e:
+            grp.align()
+        assert "k_correspondences" in str(e.value)
+    finally:
+        grp.close()

@@ -51,14 +51,19 @@ def _write_cube_ply(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,n_tests", [("ref_test_gicp_alignment", 3), ("ref_test_fod_detector", 3)])
-def test_reference_gtests_pass_on_the_gpu(tmp_path, name, n_tests):
+@pytest.mark.parametrize("name,n_tests,devices", [("ref_test_gicp_alignment", 3, None), ("ref_test_fod_detector", 3, None),
+                                                  ("ref_test_gicp_alignment", 3, "0,0")])
+def test_reference_gtests_pass_on_the_gpu(tmp_path, name, n_tests, devices):
+    """devices = "0,0": the same unmodified test with GICPB_DEVICES set - the drop-in then runs the registration as a
+    two-rank gicpb_group inside the test's process (both ranks on this box's one GPU, sums through the host)"""
     exe = os.path.join(OUT, name)
     if not os.path.isfile(exe):
         pytest.skip("oracle/_ref/%s was not built (needs /root/reference at build time)" % name)
     os.makedirs(tmp_path / "test")
     _write_cube_ply(str(tmp_path / "test" / "cube.ply"))
     env = dict(os.environ, GICPB_STUB_PKG_PATH=str(tmp_path))
+    if devices:
+        env["GICPB_DEVICES"] = devices
     run = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
     print(run.stdout[-4000:], run.stderr[-3000:])
     assert run.returncode == 0
