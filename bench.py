@@ -562,7 +562,10 @@ def run_ours(args):
                           "rows": sweep}
 
     if rank == 0:
-        h2d = int(src.nbytes + tgt.nbytes)
+        # sharded uploads (csrc/engine.cu do_prefetch): every rank uploads its 1 / world of the rows of both clouds and the
+        # slices are exchanged between the GPUs, so the whole job moves each cloud over PCIe once
+        shard_up = world > 1 and os.environ.get("GICPB_SHARD_UPLOAD", "1") != "0"
+        h2d = int(src.nbytes + tgt.nbytes) * (1 if (world == 1 or shard_up) else world)
         line = {
             "metric": "gicp_correspondences_per_s", "value": value, "unit": "correspondences/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
@@ -580,7 +583,8 @@ def run_ours(args):
                        "outer_iterations": res["outer_iterations"], "cost_evaluations": res["cost_evaluations"]},
             "align_ms": res["ms_total"], "fitness": fit,
             "e2e": {"value": e2e_value, "unit": "correspondences/s", "ms_per_step": 1e3 * e_total / len(e_times),
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 * 4 + 8 + 14 * 8 * int(e_res["cost_evaluations"])},
+                    "h2d_bytes_per_step": h2d, "h2d_bytes_per_rank": h2d // world if (world == 1 or shard_up) else h2d // world,
+                    "d2h_bytes_per_step": 16 * 4 + 8 + 14 * 8 * int(e_res["cost_evaluations"])},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

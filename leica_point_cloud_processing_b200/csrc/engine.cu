@@ -222,6 +222,8 @@ struct gicpb_ctx {
     int64_t dev_stride = 0;  // stride of the device copy (12 when the cloud went through the packed staged upload)
     cudaEvent_t done = nullptr;
     bool pending = false;
+    bool sharded = false;    // only this rank's slice of the rows was uploaded: take_prefetch gathers the other ranks'
+    int64_t chunk_rows = 0;  // rows per rank in the gathered buffer (the last rank's slice may be shorter, or empty)
   } prefetch[2];  // 0 target, 1 source
   gicpb_params prm{};
   std::string err;
@@ -800,16 +802,91 @@ void check_cloud_args(const void* p, int64_t n, int64_t stride) {
   if (reinterpret_cast<uintptr_t>(p) % 4) throw ArgError("cloud pointer must be 4-byte aligned");
 }
 
-// true: the host cloud (xyz, n, stride) was uploaded by gicpb_prefetch_cloud; the compute stream now waits for that copy
+// Sharded upload (world > 1, host clouds): every rank is given the same clouds, so each uploads only its 1 / world of the
+// rows (packed xyz, 12 bytes per point) and the slices are exchanged between the GPUs - one in-place ncclAllGather, or peer
+// copies inside a gicpb_group - instead of every rank pulling both whole clouds through its host.  GICPB_SHARD_UPLOAD=0: off.
+bool shard_uploads(const gicpb_ctx* c) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("GICPB_SHARD_UPLOAD");
+    return !(e && *e == '0');
+  }();
+  return enabled && c->world > 1 && (c->local != nullptr || c->comm != nullptr);
+}
+
+void gather_slices(gicpb_ctx* c, int which) {
+  gicpb_ctx::Prefetch& p = c->prefetch[which];
+  const size_t chunk_bytes = (size_t)p.chunk_rows * 12;
+  if (c->local) {
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));  // this rank's slice is in place (the stream waits for the copy stream)
+    c->local->barrier();
+    for (int r = 0; r < c->world; ++r) {
+      if (r == c->rank) continue;
+      const int64_t lo = std::min<int64_t>(p.n, (int64_t)r * p.chunk_rows), hi = std::min<int64_t>(p.n, lo + p.chunk_rows);
+      if (hi <= lo) continue;
+      const gicpb_ctx* o = c->local->members[(size_t)r];
+      GICPB_CUDA(cudaMemcpyPeerAsync(p.dev + (size_t)r * chunk_bytes, c->device, o->prefetch[which].dev + (size_t)r * chunk_bytes,
+                                     o->device, (size_t)(hi - lo) * 12, c->stream));
+    }
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->local->barrier();  // every rank has what it needs from the others' staging buffers
+  } else {
+    check_nccl(c, c->nccl->AllGather(p.dev + (size_t)c->rank * chunk_bytes, p.dev, chunk_bytes, /*ncclInt8*/ 0, c->comm, c->stream),
+               "ncclAllGather");
+  }
+}
+
+// starts the upload of a host cloud on the copy stream (gicpb_prefetch_cloud)
+void do_prefetch(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t stride) {
+  gicpb_ctx::Prefetch& p = c->prefetch[which];
+  if (p.pending) GICPB_CUDA(cudaEventSynchronize(p.done));
+  // the index of this cloud may still be in use on the compute stream (its staging buffer is about to be overwritten)
+  GICPB_CUDA(cudaEventRecord(c->ev_order, c->stream));
+  GICPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
+  GridIndex& g = which == 0 ? c->tgt : c->src;
+  const unsigned char* src = static_cast<const unsigned char*>(xyz);
+  p.sharded = shard_uploads(c);
+  if (p.sharded) {
+    p.chunk_rows = (n + c->world - 1) / c->world;
+    const int64_t lo = std::min<int64_t>(n, (int64_t)c->rank * p.chunk_rows), hi = std::min<int64_t>(n, lo + p.chunk_rows);
+    p.dev = g.stage((size_t)p.chunk_rows * c->world * 12);
+    p.dev_stride = 12;
+    if (hi > lo) {
+      if (stride == 12 && !HostStager::wants(src + lo * stride, hi - lo, stride))
+        GICPB_CUDA(cudaMemcpyAsync(p.dev + (size_t)lo * 12, src + lo * stride, (size_t)(hi - lo) * 12, cudaMemcpyHostToDevice,
+                                   c->copy_stream));
+      else  // wider rows, or pageable memory: packed by the host threads of the pinned ring
+        c->stager.upload(p.dev + (size_t)lo * 12, src + lo * stride, hi - lo, stride, 12, c->copy_stream);
+    }
+  } else {
+    p.dev = g.stage((size_t)n * stride);
+    p.dev_stride = stride;
+    if (HostStager::wants(xyz, n, stride)) {  // pageable: packed xyz rows (this call then lasts as long as the gather)
+      c->stager.upload(p.dev, src, n, stride, 12, c->copy_stream);
+      p.dev_stride = 12;
+    } else {
+      GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+  }
+  GICPB_CUDA(cudaEventRecord(p.done, c->copy_stream));
+  p.host = xyz;
+  p.n = n;
+  p.stride = stride;
+  p.pending = true;
+}
+
+// true: the host cloud (xyz, n, stride) was uploaded by gicpb_prefetch_cloud (or is uploaded here, in slices, when the job
+// is sharded); the compute stream now waits for that copy
 bool take_prefetch(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t stride, int on_device) {
   gicpb_ctx::Prefetch& p = c->prefetch[which];
+  if (p.pending && (on_device || p.host != xyz || p.n != n || p.stride != stride)) {
+    p.pending = false;
+    GICPB_CUDA(cudaEventSynchronize(p.done));  // a different cloud is being set: let the stale copy finish first
+  }
+  if (!p.pending && !on_device && shard_uploads(c)) do_prefetch(c, which, xyz, n, stride);
   if (!p.pending) return false;
   p.pending = false;
-  if (on_device || p.host != xyz || p.n != n || p.stride != stride) {
-    GICPB_CUDA(cudaEventSynchronize(p.done));  // a different cloud is being set: let the stale copy finish first
-    return false;
-  }
   GICPB_CUDA(cudaStreamWaitEvent(c->stream, p.done, 0));
+  if (p.sharded) gather_slices(c, which);
   return true;
 }
 
@@ -1149,25 +1226,7 @@ int gicpb_prefetch_cloud(gicpb_ctx* c, int which, const void* xyz, int64_t n, in
   return guarded(c, [&] {
     if (which != 0 && which != 1) throw ArgError("which must be 0 (target) or 1 (source)");
     check_cloud_args(xyz, n, stride);
-    gicpb_ctx::Prefetch& p = c->prefetch[which];
-    if (p.pending) GICPB_CUDA(cudaEventSynchronize(p.done));
-    // the index of this cloud may still be in use on the compute stream (its staging buffer is about to be overwritten)
-    GICPB_CUDA(cudaEventRecord(c->ev_order, c->stream));
-    GICPB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
-    GridIndex& g = which == 0 ? c->tgt : c->src;
-    p.dev = g.stage((size_t)n * stride);
-    p.dev_stride = stride;
-    if (HostStager::wants(xyz, n, stride)) {  // pageable: packed xyz rows (this call then lasts as long as the gather)
-      c->stager.upload(p.dev, static_cast<const unsigned char*>(xyz), n, stride, 12, c->copy_stream);
-      p.dev_stride = 12;
-    } else {
-      GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
-    }
-    GICPB_CUDA(cudaEventRecord(p.done, c->copy_stream));
-    p.host = xyz;
-    p.n = n;
-    p.stride = stride;
-    p.pending = true;
+    do_prefetch(c, which, xyz, n, stride);
   });
 }
 

@@ -144,11 +144,6 @@ void prefer_shared_carveout_grid();
 void prefer_shared_carveout_sort();
 
 // hand-written device-wide primitives (sort_scan.cu)
-// Stable LSD radix sort of (key, value) pairs on the low `key_bits` bits.  Returns true if the result is in
-// the *_b buffers, false if in *_a.  hist must hold 256 * ceil(n / 2048) + 1024 entries.
-bool radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, uint32_t* hist,
-                      uint32_t* scan_tmp, int64_t n, int key_bits, cudaStream_t stream);
-size_t radix_sort_hist_entries(int64_t n);
 size_t scan_tmp_entries(int64_t n);
 // exclusive prefix sum of n uint32 (in place allowed); tmp must hold scan_tmp_entries(n)
 void exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uint32_t* tmp, cudaStream_t stream);

@@ -188,7 +188,8 @@ class VoxelGrid {
               bool* overflow);
 
  private:
-  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, hist_, scan_tmp_, starts_;
+  DevBuf<uint32_t> keys_a_, keys_b_, vals_a_, vals_b_, scan_tmp_, starts_;
+  RadixSorter sorter_;
   DevBuf<unsigned> scratch_;
 };
 

@@ -337,12 +337,11 @@ int64_t VoxelGrid::run(const unsigned char* d_in, int64_t n, int64_t stride, flo
   int key_bits = 1;
   while ((1ull << key_bits) <= (unsigned long long)sentinel) ++key_bits;
   keys_a_.reserve(n); keys_b_.reserve(n); vals_a_.reserve(n); vals_b_.reserve(n);
-  hist_.reserve(radix_sort_hist_entries(n));
-  scan_tmp_.reserve(scan_tmp_entries(std::max<int64_t>((int64_t)radix_sort_hist_entries(n), n)));
+  scan_tmp_.reserve(scan_tmp_entries(n));
+  sorter_.prepare(n, stream);
   voxel_keys_kernel<<<nblk(n, 256), 256, 0, stream>>>(d_in, n, stride, vp, sentinel, keys_a_.get(), vals_a_.get());
   GICPB_LAUNCHED();
-  const bool in_b = radix_sort_pairs(keys_a_.get(), vals_a_.get(), keys_b_.get(), vals_b_.get(), hist_.get(),
-                                     scan_tmp_.get(), n, key_bits, stream);
+  const bool in_b = sorter_.sort(keys_a_.get(), vals_a_.get(), keys_b_.get(), vals_b_.get(), n, key_bits, false, stream);
   const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
   const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
   uint32_t* flags = in_b ? keys_a_.get() : keys_b_.get();
