@@ -102,6 +102,9 @@ int gicpb_get_params(const gicpb_ctx* ctx, gicpb_params* p);
 int gicpb_nccl_unique_id(const char* libnccl_path, unsigned char id_out[128]);
 int gicpb_comm_init(gicpb_ctx* ctx, const char* libnccl_path, int rank, int world, const unsigned char id[128]);
 int gicpb_comm_rank(const gicpb_ctx* ctx, int* rank, int* world);
+/* This rank's shard [lo, hi) of its sorted source points, how many source points this rank has indexed (with more than one
+ * rank: its window of brick planes, not the whole cloud) and how often a window had to be widened to the whole cloud. */
+int gicpb_shard_info(gicpb_ctx* ctx, int64_t* lo, int64_t* hi, int64_t* n_indexed_here, int64_t* widened);
 /* Optional, after gicpb_comm_init on every rank: fuse the cross-GPU sum of the 14 cost sums INTO the cost kernel over
  * NVLink peer memory (the kernel's last block stores its sums into every rank's slot block, raises a flag, waits for
  * the other ranks' flags and adds the slots in rank order), replacing the ncclAllReduce + copy per evaluation.
@@ -120,8 +123,9 @@ int gicpb_peer_disable(gicpb_ctx* ctx); /* back to ncclAllReduce (call on every 
  * process per GPU.  The collectives stay inside the process: target covariances by peer copies, the per-evaluation sum
  * fused into the cost kernel over peer memory when every pair of devices can map each other (gicpb_group_fused), else
  * through the host.  No NCCL is needed.  All clouds are HOST clouds.  A group of one device is a plain context.
- * gicpb_group_ctx(g, 0) is a full context for the single-GPU calls (transform, difference, clusters, ...); do not call
- * set_* / align / fitness on a member directly while the group is in use. */
+ * gicpb_group_ctx(g, r) is a full single-GPU context between group calls (transform, difference, clusters, resolution,
+ * normals, ...): used on its own a member never waits for the others.  Clouds set through a member directly are that
+ * member's alone; the next gicpb_group_set_clouds replaces them. */
 typedef struct gicpb_group gicpb_group;
 int gicpb_group_create(const int* devices, int n_devices, gicpb_group** out);
 void gicpb_group_destroy(gicpb_group* group);

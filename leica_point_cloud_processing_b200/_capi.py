@@ -112,6 +112,7 @@ _SIGNATURES = [
     ("gicpb_nccl_unique_id", ctypes.c_int, [ctypes.c_char_p, c_uint8_p]),
     ("gicpb_comm_init", ctypes.c_int, [_VOID_P, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, c_uint8_p]),
     ("gicpb_comm_rank", ctypes.c_int, [_VOID_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    ("gicpb_shard_info", ctypes.c_int, [_VOID_P, c_int64_p, c_int64_p, c_int64_p, c_int64_p]),
     ("gicpb_peer_export", ctypes.c_int, [_VOID_P, c_uint8_p]),
     ("gicpb_peer_import", ctypes.c_int, [_VOID_P, c_uint8_p, ctypes.c_int]),
     ("gicpb_peer_disable", ctypes.c_int, [_VOID_P]),
@@ -318,11 +319,15 @@ class Engine:
         self._check(self.lib.gicpb_comm_rank(self.h, ctypes.byref(r), ctypes.byref(w)))
         return r.value, w.value
 
+    def shard_info(self):
+        """(lo, hi, source points indexed on this rank, times a window was widened): gicpb_shard_info"""
+        v = [ctypes.c_int64() for _ in range(4)]
+        self._check(self.lib.gicpb_shard_info(self.h, *[ctypes.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
     def shard(self):
-        """[lo, hi) of the sorted source points this context owns (csrc/engine.cu update_shard)"""
-        r, w = self.comm_rank()
-        n = self.grid_info(1)["n_indexed"]
-        return n * r // w, n * (r + 1) // w
+        """[lo, hi) of this rank's sorted source points that it owns (csrc/engine.cu update_shard)"""
+        return self.shard_info()[:2]
 
     def comm_init(self, rank, world, unique_id, libnccl=None):
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)

@@ -101,6 +101,8 @@ struct GridView {
   float margin;                  // conservative slack (metres) for all box-distance lower bounds
   int nx, ny, nz;                // grid size in cells (multiples of 8)
   int nbx, nby, nbz;             // grid size in bricks
+  int bsx, bsy, bsz;             // linear brick index = bx * bsx + by * bsy + bz * bsz (default 1, nbx, nbx * nby)
+  int bo0, bo1, bo2;             // the axes (0 x, 1 y, 2 z) from the fastest to the slowest in that index (default 0, 1, 2)
   int nsx, nsy, nsz;             // grid size in superbricks
   int nhx, nhy, nhz;             // grid size in hyperbricks
   int n;                         // number of indexed (finite) points
@@ -134,7 +136,7 @@ GICPB_HD unsigned local_code(unsigned lx, unsigned ly, unsigned lz) { return (lz
 // cell coordinate of a coordinate value along one axis (NOT clamped); identical code for build and query
 GICPB_HD int cell_of(float v, float origin, float inv_h) { return floor_to_int(fmul(fsub(v, origin), inv_h)); }
 
-GICPB_HD int brick_index(const GridView& g, int bx, int by, int bz) { return (bz * g.nby + by) * g.nbx + bx; }
+GICPB_HD int brick_index(const GridView& g, int bx, int by, int bz) { return bx * g.bsx + by * g.bsy + bz * g.bsz; }
 
 // lower bound of |q - p| along one axis for any p stored in the box [lo, lo + size); never negative
 GICPB_HD float axis_gap(float q, float lo, float size, float margin) {

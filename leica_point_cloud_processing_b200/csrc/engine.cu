@@ -282,6 +282,7 @@ struct gicpb_ctx {
   double ms_corr = 0, ms_cost = 0;
   int64_t far_queries = 0;
   int64_t cost_evals = 0;
+  int64_t window_widened = 0;  // times a sharded source had to be indexed whole after all (GridIndex::widen)
 };
 
 namespace {
@@ -366,9 +367,24 @@ FarWork far_work(gicpb_ctx* c, int64_t n_items, int near_rings = kNearMaxRing) {
 }
 
 void update_shard(gicpb_ctx* c) {
+  if (c->src.ready() && c->src.plane_sharded()) {  // the rank's brick planes of the (windowed) source index
+    c->shard_lo = c->src.shard_lo();
+    c->shard_hi = c->src.shard_hi();
+    return;
+  }
   const int64_t n = c->src.ready() ? c->src.n_indexed() : 0;
   c->shard_lo = (int)(n * c->rank / c->world);
   c->shard_hi = (int)(n * (c->rank + 1) / c->world);
+}
+
+// Sharded jobs index only the rank's window of the source (GridIndex::build, world > 1); GICPB_WINDOWED_SOURCE=0: the whole
+// source on every rank, as for the target.
+int source_world(const gicpb_ctx* c) {
+  static const bool enabled = [] {
+    const char* e = std::getenv("GICPB_WINDOWED_SOURCE");
+    return !(e && *e == '0');
+  }();
+  return enabled ? c->world : 1;
 }
 
 // Target covariances are needed in full on every rank, but each is a function of the target cloud alone: every rank
@@ -413,9 +429,29 @@ void finish_covariances(gicpb_ctx* c) {
     check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
                                      kNcclFloat64, c->comm, c->stream), "ncclAllGather");
   }
-  launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream);
+  const GridIndex::KnnWindow win = c->src.knn_window();
+  unsigned* violations = c->far_counter.get() + 2;  // far_work() reserved 4 words; [0..1] belong to the far hand-over
+  if (win.axis >= 0) {
+    GICPB_CUDA(cudaMemsetAsync(violations, 0, sizeof(unsigned), c->stream));
+    launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream, &win,
+                           violations);
+    GICPB_CUDA(cudaMemcpyAsync(c->h_far + 2, violations, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr, fw, c->stream);
+  }
   GICPB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->world > 1 && c->local) c->local->barrier();  // nobody touches its n_tgt again before every copy out of it is done
+  if (win.axis >= 0 && c->h_far[2] != 0u) {
+    // some neighbourhoods of this rank's shard reach beyond the halo of its window (a sparse region): index the whole source
+    // after all - the shard stays the same set of points - and take the covariances from that
+    c->src.widen(c->stream);
+    update_shard(c);
+    c->n_src.reserve(3 * (size_t)std::max(c->shard_hi - c->shard_lo, 1));
+    launch_knn_covariances(c->src.view(), c->shard_lo, c->shard_hi, k, c->n_src.get(), nullptr, nullptr,
+                           far_work(c, std::max(chunk, c->shard_hi - c->shard_lo)), c->stream);
+    GICPB_CUDA(cudaStreamSynchronize(c->stream));
+    ++c->window_widened;
+  }
   c->cov_ready = true;
   c->pairs_valid = false;
 }
@@ -425,7 +461,7 @@ void ensure_covariances(gicpb_ctx* c) {
   if (!c->tgt.ready() || !c->src.ready()) throw StateError("set_target and set_source must be called first");
   check_k(c);
   const int k = c->prm.k_correspondences;
-  if (k > c->tgt.n_indexed() || k > c->src.n_indexed())
+  if (k > c->tgt.n_indexed() || k > c->src.n_finite_total())
     throw AlignStop(GICPB_E_TOO_FEW_POINTS, "k_correspondences exceeds the number of points in a cloud");
   start_target_cov(c, c->stream);
   finish_covariances(c);
@@ -687,7 +723,7 @@ void do_align(gicpb_ctx* c, gicpb_align_result* out) {
 
   while (!converged) {
     run_correspondences(c, T, nr_iterations == 0);
-    corr_queries += c->src.n_indexed();
+    corr_queries += c->src.n_finite_total();
     std::memcpy(prev, T, sizeof(T));
     CostSession session(c);  // resident evaluation kernel for this inner solve (queued behind the correspondence kernels)
 
@@ -897,11 +933,26 @@ GridIndex& pick_grid(gicpb_ctx* c, int which) {
   throw ArgError("which must be 0 (target), 1 (source) or 2 (subtract)");
 }
 
+// the calls that look at a WHOLE cloud (resolution, normals, the kNN hook): a source of which only this rank's window is
+// indexed is indexed whole first
+GridIndex& pick_whole_grid(gicpb_ctx* c, int which) {
+  GridIndex& g = pick_grid(c, which);
+  if (g.ready() && g.windowed()) {
+    g.widen(c->stream);
+    if (which == 1) {
+      update_shard(c);
+      c->cov_ready = false;
+      c->pairs_valid = false;
+    }
+  }
+  return g;
+}
+
 // Utils::getNormals on an indexed cloud: (nx, ny, nz, curvature) per point in ORIGINAL order into c->io_b (float4 rows, NaN x 4
 // where PCL gives no normal); returns the number of finite normals, *total_points = rows written
 int64_t compute_normals(gicpb_ctx* c, int which, double radius, int64_t* total_points) {
   if (!(radius > 0)) throw ArgError("radius must be > 0");
-  GridIndex& g = pick_grid(c, which);
+  GridIndex& g = pick_whole_grid(c, which);
   if (!g.ready()) throw StateError("cloud not set");
   const int64_t total = g.n_points();
   const int n = g.n_indexed();
@@ -961,7 +1012,14 @@ int group_run(gicpb_group* g, F fn) {  // fn(rank, ctx) -> status, on one thread
   std::vector<int> rc((size_t)n, GICPB_OK);
   g->lg.reset();
   auto body = [&](int r) {
-    rc[(size_t)r] = fn(r, g->ctx[(size_t)r]);
+    // a member is rank r of n only while a group call runs on all members at once; used on its own (gicpb_group_ctx) it is
+    // a plain single-GPU context, so that nothing it does waits for the other members
+    gicpb_ctx* c = g->ctx[(size_t)r];
+    c->rank = r;
+    c->world = n;
+    rc[(size_t)r] = fn(r, c);
+    c->rank = 0;
+    c->world = 1;
     if (rc[(size_t)r] != GICPB_OK) g->lg.fail();  // the others must not wait for this rank at a barrier
   };
   std::vector<std::thread> th;
@@ -1008,6 +1066,10 @@ void gicpb_default_params(gicpb_params* p) {
   p->l2_persist = 1;
   p->cost_moments = 0;
   p->cost_persistent = 1;
+  // GICPB_COST_PERSISTENT=0: one launch per evaluation (for runs under a profiler, which serialises launches and keeps the
+  // host from talking to a resident kernel: every inner solve would first idle out, 200 ms, and then fall back)
+  if (const char* e = std::getenv("GICPB_COST_PERSISTENT"))
+    if (*e == '0') p->cost_persistent = 0;
 }
 
 int gicpb_create(int device, gicpb_ctx** out) {
@@ -1215,6 +1277,15 @@ int gicpb_peer_disable(gicpb_ctx* c) {
   return GICPB_OK;
 }
 
+int gicpb_shard_info(gicpb_ctx* c, int64_t* lo, int64_t* hi, int64_t* n_indexed_here, int64_t* widened) {
+  if (!c) return GICPB_E_BADARG;
+  if (lo) *lo = c->shard_lo;
+  if (hi) *hi = c->shard_hi;
+  if (n_indexed_here) *n_indexed_here = c->src.ready() ? c->src.n_indexed() : 0;
+  if (widened) *widened = c->window_widened;
+  return GICPB_OK;
+}
+
 int gicpb_comm_rank(const gicpb_ctx* c, int* rank, int* world) {
   if (!c) return GICPB_E_BADARG;
   if (rank) *rank = c->rank;
@@ -1254,7 +1325,8 @@ int gicpb_set_source(gicpb_ctx* c, const void* xyz, int64_t n, int64_t stride, i
       stride = c->prefetch[1].dev_stride;
       on_device = 1;
     }
-    c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
+    c->src.build(xyz, n, stride, on_device != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager, c->rank,
+                 source_world(c));
     update_shard(c);
   });
 }
@@ -1290,14 +1362,15 @@ int gicpb_set_clouds(gicpb_ctx* c, const void* target, int64_t n_target, int64_t
         source_stride = c->prefetch[1].dev_stride;
         s_dev = 1;
       }
-      c->src.build(source, n_source, source_stride, s_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager);
+      c->src.build(source, n_source, source_stride, s_dev != 0, c->prm.cell_size, c->prm.points_per_cell, c->stream, &c->stager,
+                   c->rank, source_world(c));
     } catch (...) {
       if (overlap) cudaStreamSynchronize(c->aux_stream);  // nothing may still be running on the target when we leave
       throw;
     }
     if (overlap) {
       GICPB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
-      if (k <= c->src.n_indexed()) {
+      if (k <= c->src.n_finite_total()) {
         finish_covariances(c);
       } else {
         GICPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -1431,7 +1504,7 @@ int gicpb_knn(gicpb_ctx* c, int which, int32_t* idx, float* d2) {
   return guarded(c, [&] {
     if (!idx || !d2) throw ArgError("null output");
     if (which != 0 && which != 1) throw ArgError("which must be 0 or 1");
-    GridIndex& g = pick_grid(c, which);
+    GridIndex& g = pick_whole_grid(c, which);
     if (!g.ready()) throw StateError("cloud not set");
     const int k = c->prm.k_correspondences;
     const int n = g.n_indexed();
@@ -1561,7 +1634,7 @@ int gicpb_cost(gicpb_ctx* c, const double x[6], double* f, double g[6]) {
 int gicpb_cloud_resolution(gicpb_ctx* c, int which, double* resolution) {
   return guarded(c, [&] {
     if (!resolution) throw ArgError("null output");
-    GridIndex& g = pick_grid(c, which);
+    GridIndex& g = pick_whole_grid(c, which);
     if (!g.ready()) throw StateError("cloud not set");
     const int n = g.n_indexed();
     const FarWork fw = far_work(c, n);
@@ -1912,9 +1985,7 @@ int gicpb_group_create(const int* devices, int n_devices, gicpb_group** out) {
     for (int r = 0; r < n_devices; ++r) {
       gicpb_ctx* c = g->ctx[(size_t)r];
       DeviceGuard guard(c->device);
-      c->rank = r;
-      c->world = n_devices;
-      c->local = &g->lg;
+      c->local = &g->lg;  // rank / world are set for the duration of each group call (group_run)
       if (!fused) continue;
       for (int b = 0; b < n_devices; ++b) {
         if (b == r) continue;

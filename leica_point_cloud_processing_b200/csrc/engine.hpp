@@ -103,8 +103,25 @@ class GridIndex {
   };
   // `raw` points at the first x; device pointer iff on_device.  cell_size <= 0 -> from density.
   // stager (nullable): pageable host clouds are uploaded through it as packed xyz rows (upload.hpp)
+  // world > 1 (the SOURCE of a sharded job): only the part of the cloud that rank `rank` needs is indexed - a window of
+  // brick planes along the longest axis holding about 1 / world of the points (the rank's shard, [shard_lo, shard_hi) of
+  // the sorted points) plus one halo plane either side, so that the k nearest neighbours of the shard's points are
+  // in it (knn_window() tells the kNN kernel where the window ends; it reports every point it cannot vouch for, and the
+  // caller then widens the window to the whole cloud with widen()).  Same grid geometry, keys and order as the whole
+  // cloud's index: the window IS that index cut to its planes (bricks are numbered plane by plane for this).
   void build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
-             float points_per_cell, cudaStream_t stream, HostStager* stager = nullptr);
+             float points_per_cell, cudaStream_t stream, HostStager* stager = nullptr, int rank = 0, int world = 1);
+  void widen(cudaStream_t stream);  // re-index with the window = the whole cloud (the shard stays the same set of points)
+  bool windowed() const { return win_.active && !(win_.w_lo == 0 && win_.w_hi == win_.planes); }
+  bool plane_sharded() const { return win_.active; }  // the shard is a range of brick planes (else: an index range)
+  int shard_lo() const { return win_.shard_lo; }
+  int shard_hi() const { return win_.shard_hi; }
+  int64_t n_finite_total() const { return win_.n_finite; }  // finite points of the whole cloud
+  struct KnnWindow {  // the window along `axis` in coordinates: neighbours beyond [lo, hi] are not indexed (axis -1: none)
+    int axis = -1;
+    float lo = 0.f, hi = 0.f;
+  };
+  KnnWindow knn_window() const;
   bool ready() const { return ready_; }
   const GridView& view() const { return view_; }
   const Info& info() const { return info_; }
@@ -136,6 +153,22 @@ class GridIndex {
   DevBuf<float> brick_plane_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
   unsigned* h_pin_ = nullptr; // pinned host words the build reads its counters back into
+  // sharded source (world > 1)
+  struct Window {
+    bool active = false;
+    int rank = 0, world = 1, axis = 0, planes = 0;
+    int own_lo = 0, own_hi = 0, w_lo = 0, w_hi = 0;  // brick planes along `axis`: owned [own_lo, own_hi), indexed [w_lo, w_hi)
+    int shard_lo = 0, shard_hi = 0;
+    int64_t n_finite = 0;
+    std::vector<uint32_t> plane_prefix;                // [planes + 1] finite points in the planes before each
+  } win_;
+  DevBuf<float4> pts_local_;
+  DevBuf<uint32_t> plane_hist_, win_flags_, win_pos_;
+  GridView geom_{};                                    // grid geometry of the whole cloud (pointers unset)
+  int64_t n_all_ = 0;
+  void index_points(const float4* pts, int64_t n_in, int64_t n_valid, const GridView& geom, cudaStream_t stream, void* trace);
+  void set_window(int w_lo, int w_hi);
+  const float4* window_points(cudaStream_t stream, int64_t* n_local);
 };
 
 // the index-build kernels ask for the largest shared-memory carve-out, like the kNN kernel they may share an SM with

@@ -170,19 +170,64 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4* __restrict__ pt
 }
 
 // gather the points into sorted order and record the inverse permutation (original index -> sorted position;
-// the tail of vals, i >= n_valid, holds the non-finite points: position -1)
+// the tail of vals, i >= n_valid, holds the non-finite points: position -1).  The original index is the point's w.
 __global__ void __launch_bounds__(256) reorder_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals,
                                                        int64_t n_valid, int64_t n, float4* __restrict__ sorted,
                                                        int* __restrict__ pos_of) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t oi = vals[i];
+  const float4 p = pts[vals[i]];
+  const int oi = __float_as_int(p.w);
   if (i < n_valid) {
-    sorted[i] = pts[oi];
+    sorted[i] = p;
     pos_of[oi] = (int)i;
   } else {
     pos_of[oi] = -1;
   }
+}
+
+// ---- sharded source: the window of brick planes one rank indexes (engine.hpp GridIndex::build, world > 1) ------------------
+__device__ __forceinline__ int plane_of(const GridView& g, int axis, const float4& p) {
+  const float v = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+  const float o = axis == 0 ? g.ox : (axis == 1 ? g.oy : g.oz);
+  const int dim = axis == 0 ? g.nx : (axis == 1 ? g.ny : g.nz);
+  return clampi(cell_of(v, o, g.inv_h), 0, dim - 1) >> kBrickShift;
+}
+
+// finite points per brick plane along `axis` (planes <= 8192: one shared-memory histogram per block)
+__global__ void __launch_bounds__(256) plane_hist_kernel(const float4* __restrict__ pts, int64_t n, GridView g, int axis,
+                                                          int planes, uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t s_hist[];
+  for (int i = threadIdx.x; i < planes; i += 256) s_hist[i] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float4 p = pts[i];
+    if (finite3(p.x, p.y, p.z)) atomicAdd(&s_hist[plane_of(g, axis, p)], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < planes; i += 256)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(256) window_flags_kernel(const float4* __restrict__ pts, int64_t n, GridView g, int axis,
+                                                            int w_lo, int w_hi, uint32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  bool in = false;
+  if (finite3(p.x, p.y, p.z)) {
+    const int pl = plane_of(g, axis, p);
+    in = pl >= w_lo && pl < w_hi;
+  }
+  flags[i] = in ? 1u : 0u;
+}
+
+// stable: pos = exclusive scan of the flags, so the window keeps the cloud's order (and the index its order inside a cell)
+__global__ void __launch_bounds__(256) window_gather_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ flags,
+                                                             const uint32_t* __restrict__ pos, int64_t n,
+                                                             float4* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flags[i]) out[pos[i]] = pts[i];
 }
 
 // brick table from the occupancy marks (rank = exclusive scan of occ): slot = rank of the brick among the occupied bricks
@@ -202,7 +247,18 @@ __global__ void __launch_bounds__(256) brick_table_kernel(const uint32_t* __rest
     return;
   }
   brick_slot[b] = (int)r;
-  const int bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
+  // b = bx * bsx + by * bsy + bz * bsz: peel the axes off from the slowest (g.bo2) to the fastest (g.bo0)
+  int v[3];
+  {
+    const int s[3] = {g.bsx, g.bsy, g.bsz};
+    int rest = b;
+    v[g.bo2] = rest / s[g.bo2];
+    rest -= v[g.bo2] * s[g.bo2];
+    v[g.bo1] = rest / s[g.bo1];
+    rest -= v[g.bo1] * s[g.bo1];
+    v[g.bo0] = rest;
+  }
+  const int bx = v[0], by = v[1], bz = v[2];
   const int sx = bx >> 2, sy = by >> 2, sz = bz >> 2;
   atomicOr(&sb_mask[((size_t)sz * g.nsy + sy) * g.nsx + sx], 1ull << (((bz & 3) << 4) | ((by & 3) << 2) | (bx & 3)));
   atomicOr(&hb_mask[((size_t)(sz >> 2) * g.nhy + (sy >> 2)) * g.nhx + (sx >> 2)],
@@ -393,6 +449,9 @@ void prefer_shared_carveout_grid() {
   cudaFuncSetAttribute(popcount_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(keys_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(reorder_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(plane_hist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(window_flags_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(window_gather_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(brick_table_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(cell_heads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(cell_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -400,8 +459,18 @@ void prefer_shared_carveout_grid() {
   (void)cudaGetLastError();
 }
 
+// brick planes (8 cells each) indexed either side of a rank's own planes; GICPB_HALO_PLANES=0 makes the kNN check fail at
+// every window edge (a test of the fall-back to the whole cloud)
+static int halo_planes() {
+  static const int v = [] {
+    const char* e = std::getenv("GICPB_HALO_PLANES");
+    return e && *e ? std::max(0, std::atoi(e)) : 1;
+  }();
+  return v;
+}
+
 void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_device, float cell_size,
-                      float points_per_cell, cudaStream_t stream, HostStager* stager) {
+                      float points_per_cell, cudaStream_t stream, HostStager* stager, int rank, int world) {
   const auto t_begin = std::chrono::steady_clock::now();
   BuildTrace trace(stream);
   trace.mark("begin");
@@ -540,17 +609,151 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   g.nhx = (g.nsx + 3) / 4;
   g.nhy = (g.nsy + 3) / 4;
   g.nhz = (g.nsz + 3) / 4;
-  const size_t n_sb = (size_t)g.nsx * g.nsy * g.nsz, n_hb = (size_t)g.nhx * g.nhy * g.nhz;
-
+  g.bsx = 1;
+  g.bsy = bd[0];
+  g.bsz = bd[0] * bd[1];
+  g.bo0 = 0;
+  g.bo1 = 1;
+  g.bo2 = 2;
   trace.mark("probe");
-  // ---- keys (+ brick occupancy + digit histograms) -> brick table -> sort -> reorder ------------------------------
+
+  // ---- sharded source: brick planes along the longest axis, numbered slowest, and this rank's window of them ---------
+  win_ = Window{};
+  win_.n_finite = n_valid;
+  n_all_ = n;
+  if (world > 1) {
+    int axis = 0;
+    if (bd[1] > bd[axis]) axis = 1;
+    if (bd[2] > bd[axis]) axis = 2;
+    const int planes = bd[axis];
+    if (planes >= 4 * world && planes <= 8192 && n_valid >= 1024 * (int64_t)world) {
+      const int o0 = axis == 0 ? 1 : 0, o1 = axis == 2 ? 1 : 2;  // the other two axes, in x < y < z order
+      int strides[3];
+      strides[o0] = 1;
+      strides[o1] = bd[o0];
+      strides[axis] = bd[o0] * bd[o1];
+      g.bsx = strides[0];
+      g.bsy = strides[1];
+      g.bsz = strides[2];
+      g.bo0 = o0;
+      g.bo1 = o1;
+      g.bo2 = axis;
+      plane_hist_.reserve((size_t)planes);
+      GICPB_CUDA(cudaMemsetAsync(plane_hist_.get(), 0, (size_t)planes * sizeof(uint32_t), stream));
+      plane_hist_kernel<<<std::min<unsigned>(blocks_for(n, 256 * 8), 148u * 4u), 256, (size_t)planes * sizeof(uint32_t), stream>>>(
+          pts_unsorted_.get(), n, g, axis, planes, plane_hist_.get());
+      GICPB_LAUNCHED();
+      std::vector<uint32_t> hist((size_t)planes);
+      GICPB_CUDA(cudaMemcpyAsync(hist.data(), plane_hist_.get(), (size_t)planes * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      GICPB_CUDA(cudaStreamSynchronize(stream));
+      win_.plane_prefix.assign((size_t)planes + 1, 0u);
+      for (int p = 0; p < planes; ++p) win_.plane_prefix[(size_t)p + 1] = win_.plane_prefix[(size_t)p] + hist[(size_t)p];
+      // rank r owns the planes [cut(r), cut(r + 1)): cut(r) = first plane with at least r / world of the points before it
+      auto cut = [&](int r) {
+        if (r <= 0) return 0;
+        if (r >= world) return planes;
+        const uint64_t want = (uint64_t)n_valid * (uint64_t)r / (uint64_t)world;
+        int p = 0;
+        while (p < planes && win_.plane_prefix[(size_t)p] < want) ++p;
+        return p;
+      };
+      bool every_rank_owns_points = true;
+      for (int r = 0; r < world; ++r)
+        if (win_.plane_prefix[(size_t)cut(r + 1)] == win_.plane_prefix[(size_t)cut(r)]) every_rank_owns_points = false;
+      if (every_rank_owns_points) {
+        win_.active = true;
+        win_.rank = rank;
+        win_.world = world;
+        win_.axis = axis;
+        win_.planes = planes;
+        win_.own_lo = cut(rank);
+        win_.own_hi = cut(rank + 1);
+        set_window(std::max(0, win_.own_lo - halo_planes()), std::min(planes, win_.own_hi + halo_planes()));
+      } else {  // degenerate split: index everything, shards by index range (the default numbering again)
+        g.bsx = 1; g.bsy = bd[0]; g.bsz = bd[0] * bd[1];
+        g.bo0 = 0; g.bo1 = 1; g.bo2 = 2;
+      }
+    }
+    trace.mark("window");
+  }
+  geom_ = g;
+  int64_t n_local = 0;
+  const float4* pts_in = pts_unsorted_.get();
+  int64_t n_in = n, n_valid_in = n_valid;
+  if (windowed()) {
+    pts_in = window_points(stream, &n_local);
+    n_in = n_valid_in = n_local;
+  }
+  index_points(pts_in, n_in, n_valid_in, geom_, stream, &trace);
+  info_.ms_build =
+      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  trace.report(n, info_.ms_build);
+}
+
+void GridIndex::set_window(int w_lo, int w_hi) {
+  win_.w_lo = w_lo;
+  win_.w_hi = w_hi;
+  win_.shard_lo = (int)(win_.plane_prefix[(size_t)win_.own_lo] - win_.plane_prefix[(size_t)w_lo]);
+  win_.shard_hi = (int)(win_.plane_prefix[(size_t)win_.own_hi] - win_.plane_prefix[(size_t)w_lo]);
+}
+
+GridIndex::KnnWindow GridIndex::knn_window() const {
+  KnnWindow w;
+  if (!windowed()) return w;
+  const float o = win_.axis == 0 ? geom_.ox : (win_.axis == 1 ? geom_.oy : geom_.oz);
+  const float hb = geom_.h * 8.0f;
+  w.axis = win_.axis;
+  w.lo = win_.w_lo > 0 ? o + (float)win_.w_lo * hb : -INFINITY;
+  w.hi = win_.w_hi < win_.planes ? o + (float)win_.w_hi * hb : INFINITY;
+  return w;
+}
+
+// the points of the window's planes, in the cloud's order
+const float4* GridIndex::window_points(cudaStream_t stream, int64_t* n_local) {
+  const int64_t n = n_all_;
+  *n_local = (int64_t)(win_.plane_prefix[(size_t)win_.w_hi] - win_.plane_prefix[(size_t)win_.w_lo]);
+  win_flags_.reserve((size_t)n);
+  win_pos_.reserve((size_t)n);
+  scan_tmp_.reserve(scan_tmp_entries(n));
+  pts_local_.reserve((size_t)std::max<int64_t>(*n_local, 1));
+  window_flags_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), n, geom_, win_.axis, win_.w_lo, win_.w_hi,
+                                                             win_flags_.get());
+  GICPB_LAUNCHED();
+  exclusive_scan_u32(win_flags_.get(), win_pos_.get(), n, scan_tmp_.get(), stream);
+  window_gather_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), win_flags_.get(), win_pos_.get(), n,
+                                                              pts_local_.get());
+  GICPB_LAUNCHED();
+  return pts_local_.get();
+}
+
+void GridIndex::widen(cudaStream_t stream) {
+  if (!windowed()) return;
+  ready_ = false;
+  set_window(0, win_.planes);
+  index_points(pts_unsorted_.get(), n_all_, win_.n_finite, geom_, stream, nullptr);
+}
+
+// keys (+ brick occupancy + digit histograms) -> brick table -> sort -> reorder -> cell table -> brick slabs, for the points
+// `pts` (w = original index; the first n_valid in the sort order are the finite ones) on the grid `geom`
+void GridIndex::index_points(const float4* pts, int64_t n, int64_t n_valid, const GridView& geom, cudaStream_t stream,
+                             void* trace_ptr) {
+  BuildTrace none(stream);
+  none.on = false;
+  BuildTrace& trace = trace_ptr ? *static_cast<BuildTrace*>(trace_ptr) : none;
+  GridView g = geom;
+  g.n = (int)n_valid;
+  const int64_t n_bricks = (int64_t)g.nbx * g.nby * g.nbz;
+  const size_t n_sb = (size_t)g.nsx * g.nsy * g.nsz, n_hb = (size_t)g.nhx * g.nhy * g.nhz;
+  unsigned* hs = h_pin_;
+  constexpr size_t kHsBytes = 16 * sizeof(unsigned);
+  pts_sorted_.reserve((size_t)std::max<int64_t>(n, 1));
   keys_a_.reserve(n);
   keys_b_.reserve(n);
   vals_a_.reserve(n);
   vals_b_.reserve(n);
   occ_.reserve(n_bricks);
   brick_rank_.reserve(n_bricks);
-  scan_tmp_.reserve(scan_tmp_entries(n_bricks));
+  scan_tmp_.reserve(scan_tmp_entries(std::max<int64_t>(n_bricks, n_all_)));
   brick_slot_.reserve(n_bricks);
   sb_mask_.reserve(n_sb);
   hb_mask_.reserve(n_hb);
@@ -561,8 +764,9 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   GICPB_CUDA(cudaMemsetAsync(occ_.get(), 0, (size_t)n_bricks * sizeof(uint32_t), stream));
   GICPB_CUDA(cudaMemsetAsync(sb_mask_.get(), 0, n_sb * sizeof(unsigned long long), stream));
   GICPB_CUDA(cudaMemsetAsync(hb_mask_.get(), 0, n_hb * sizeof(unsigned long long), stream));
+  GICPB_CUDA(cudaMemsetAsync(scratch_.get() + 7, 0, 2 * sizeof(unsigned), stream));  // slot and cell counters
   keys_kernel<<<std::min<unsigned>(blocks_for(n, 256 * 4), 148u * 4u), 256, 0, stream>>>(
-      pts_unsorted_.get(), n, g, sentinel, (key_bits + 7) / 8, keys_a_.get(), vals_a_.get(), occ_.get(), sorter_.hist());
+      pts, n, g, sentinel, (key_bits + 7) / 8, keys_a_.get(), vals_a_.get(), occ_.get(), sorter_.hist());
   GICPB_LAUNCHED();
   trace.mark("keys");
   exclusive_scan_u32(occ_.get(), brick_rank_.get(), n_bricks, scan_tmp_.get(), stream);
@@ -579,9 +783,10 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   const uint32_t* skeys = in_b ? keys_b_.get() : keys_a_.get();
   const uint32_t* svals = in_b ? vals_b_.get() : vals_a_.get();
   trace.mark("sort");
-  pos_of_.reserve(n);
-  reorder_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts_unsorted_.get(), svals, n_valid, n, pts_sorted_.get(),
-                                                         pos_of_.get());
+  pos_of_.reserve((size_t)n_all_);
+  if (n < n_all_)  // a window: the points outside it have no position
+    GICPB_CUDA(cudaMemsetAsync(pos_of_.get(), 0xff, (size_t)n_all_ * sizeof(int), stream));
+  reorder_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(pts, svals, n_valid, n, pts_sorted_.get(), pos_of_.get());
   GICPB_LAUNCHED();
 
   trace.mark("reorder");
@@ -614,16 +819,14 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   g.sb_mask = sb_mask_.get();
   g.hb_mask = hb_mask_.get();
   view_ = g;
-  info_.cell_size = h;
-  info_.dims[0] = dims[0];
-  info_.dims[1] = dims[1];
-  info_.dims[2] = dims[2];
+  info_.n_indexed = n_valid;
+  info_.cell_size = g.h;
+  info_.dims[0] = g.nx;
+  info_.dims[1] = g.ny;
+  info_.dims[2] = g.nz;
   info_.n_bricks_occupied = n_slots;
   info_.n_cells_occupied = hs[8];
-  info_.ms_build =
-      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
   ready_ = true;
-  trace.report(n, info_.ms_build);
 }
 
 }  // namespace gicpb

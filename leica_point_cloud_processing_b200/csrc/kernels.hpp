@@ -114,8 +114,11 @@ void launch_normals_solve(const GridView& g, const unsigned* counts, const unsig
 // self-kNN (k <= 32) of sorted points [lo, hi) of grid g + regularised covariance normal per point.
 // normals: 3 doubles per point, index (i - lo).  knn_idx / knn_d2 (nullable): k entries per point, row
 // (i - lo), original indices.
+// win (nullable, with win_violations): the index only holds the window's points (GridIndex::knn_window); *win_violations counts
+// the points of [lo, hi) whose list cannot be vouched for (must be zeroed by the caller).
 void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* normals, int* knn_idx, float* knn_d2,
-                            const FarWork& fw, cudaStream_t stream);
+                            const FarWork& fw, cudaStream_t stream, const GridIndex::KnnWindow* win = nullptr,
+                            unsigned* win_violations = nullptr);
 
 // ---- cost.cu ------------------------------------------------------------------------------------------
 constexpr int kCostSums = 14;  // f, g_t[3], Rsum[9], pair count

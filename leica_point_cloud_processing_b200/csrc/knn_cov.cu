@@ -13,6 +13,7 @@
 // [j * blockDim + t], conflict-free), inserting only candidates that beat the current k-th.  The cells are visited
 // in Chebyshev rings around the query's cell (the 3x3x3 box, then shells 2..kKnnMaxRing cut to the ball of the k-th
 // distance); a query whose k-th neighbour is farther than that restarts on the hierarchical traversal (common.cuh).
+#include <atomic>
 #include <climits>
 
 #include "kernels.hpp"
@@ -59,7 +60,9 @@ template <bool kFar>
 __global__ void __launch_bounds__(kFar ? kKnnFarThreads : kKnnNearThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
                                                                double* __restrict__ normals,
                                                                int* __restrict__ knn_idx,
-                                                               float* __restrict__ knn_d2, FarWork fw) {
+                                                               float* __restrict__ knn_d2, FarWork fw, int win_axis,
+                                                               float win_lo, float win_hi,
+                                                               unsigned* __restrict__ win_violations) {
   extern __shared__ __align__(8) int smem[];
   constexpr int kKnnThreads = kFar ? kKnnFarThreads : kKnnNearThreads;
   KnnVisitor<kKnnThreads> L;
@@ -80,6 +83,15 @@ __global__ void __launch_bounds__(kFar ? kKnnFarThreads : kKnnNearThreads) knn_c
   } else if (!knn_near<kKnnThreads, kKnnQueueCap>(g, q, L, qb, qe)) {
     fw.flags[item] = 1;
     return;
+  }
+  if (win_axis >= 0) {
+    // A windowed index (sharded source) only holds the points between win_lo and win_hi along win_axis: the list is the
+    // cloud's k nearest only if the k-th of them is no farther than the nearer end of the window.  Every point this
+    // cannot be said of is counted; the caller then indexes the whole cloud instead.
+    const float v = win_axis == 0 ? qp.x : (win_axis == 1 ? qp.y : qp.z);
+    const float gap = fsub(fminf(fsub(v, win_lo), fsub(win_hi, v)), g.margin);
+    const float kd = L.count == k ? L.d2_at(k - 1) : __int_as_float(0x7f800000);
+    if (!(gap > 0.f && kd <= fmul(fmul(gap, gap), 0.999999f))) atomicAdd(win_violations, 1u);
   }
   if (knn_idx) {
     for (int j = 0; j < k; ++j) {
@@ -154,7 +166,9 @@ __global__ void __launch_bounds__(kFar ? kKnnFarThreads : kKnnNearThreads) knn_c
 }  // namespace
 
 void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* normals, int* knn_idx, float* knn_d2,
-                            const FarWork& fw, cudaStream_t stream) {
+                            const FarWork& fw, cudaStream_t stream, const GridIndex::KnnWindow* win, unsigned* win_violations) {
+  const int win_axis = (win && win_violations) ? win->axis : -1;
+  const float win_lo = win ? win->lo : 0.f, win_hi = win ? win->hi : 0.f;
   const int n = hi - lo;
   if (n <= 0) return;
   reset_far(fw, n, stream);
@@ -162,16 +176,18 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   const size_t heap = (size_t)2 * k * kKnnFarThreads * sizeof(int);
   const size_t queue = (size_t)2 * kKnnQueueCap * kKnnNearThreads * sizeof(unsigned);
   const unsigned nb = (unsigned)((n + kKnnNearThreads - 1) / kKnnNearThreads);
-  static unsigned long long attr_set = 0ull;  // one bit per device: the attribute belongs to the device's context
+  static std::atomic<unsigned long long> attr_set{0ull};  // one bit per device: the attribute belongs to the device's context
   int dev = 0;
   GICPB_CUDA(cudaGetDevice(&dev));
-  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {  // up to 88 KB of dynamic shared memory at k = 32
+  if (dev >= 64 || !((attr_set.load() >> dev) & 1ull)) {  // up to 88 KB of dynamic shared memory at k = 32
     GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (dev < 64) attr_set |= 1ull << dev;
+    if (dev < 64) attr_set.fetch_or(1ull << dev);
   }
-  knn_cov_kernel<false><<<nb, kKnnNearThreads, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
+  knn_cov_kernel<false><<<nb, kKnnNearThreads, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis,
+                                                                            win_lo, win_hi, win_violations);
   GICPB_LAUNCHED();
-  knn_cov_kernel<true><<<fw.far_blocks, kKnnFarThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw);
+  knn_cov_kernel<true><<<fw.far_blocks, kKnnFarThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis, win_lo,
+                                                                        win_hi, win_violations);
   GICPB_LAUNCHED();
 }
 

@@ -47,6 +47,8 @@ static void build_index(const std::vector<float3>& in, float h, HostIndex& ix) {
   g.margin = h * (0.002f + 5e-7f * (float)maxdim) + 4e-6f * max_abs;
   g.nx = dims[0]; g.ny = dims[1]; g.nz = dims[2];
   g.nbx = bd[0]; g.nby = bd[1]; g.nbz = bd[2];
+  g.bsx = 1; g.bsy = bd[0]; g.bsz = bd[0] * bd[1];
+  g.bo0 = 0; g.bo1 = 1; g.bo2 = 2;
   g.nsx = (bd[0] + 3) / 4; g.nsy = (bd[1] + 3) / 4; g.nsz = (bd[2] + 3) / 4;
   g.nhx = (g.nsx + 3) / 4; g.nhy = (g.nsy + 3) / 4; g.nhz = (g.nsz + 3) / 4;
   g.n = (int)in.size();

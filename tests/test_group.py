@@ -51,9 +51,14 @@ def _check_group(devices, oracle, engine):
             one = engine.align()
             assert one["outer_iterations"] == res["outer_iterations"], name
             assert np.allclose(one["transform"], res["transform"], atol=1e-6), name
-            # every member holds its shard: the shards tile the source
-            n_src = sum(grp.member(r).shard()[1] - grp.member(r).shard()[0] for r in range(grp.size))
-            assert n_src == len(s), name
+            # every member holds its shard: the shards tile the source; with several ranks a big enough source is indexed in
+            # windows (the rank's brick planes + a halo), never widened on these clouds
+            info = [grp.member(r).shard_info() for r in range(grp.size)]
+            assert sum(hi - lo for lo, hi, _, _ in info) == len(s), name
+            if grp.size > 1 and name.startswith("panel"):
+                assert all(here < len(s) for _, _, here, _ in info), info
+                assert sum(here for _, _, here, _ in info) < 2 * len(s), info
+                assert all(w == 0 for _, _, _, w in info), info
     finally:
         grp.close()
         engine.set_params(max_corr_distance=4e-2, transformation_epsilon=4e-3)
@@ -86,3 +91,35 @@ def test_group_reports_the_failing_rank(oracle):
         assert "k_correspondences" in str(e.value)
     finally:
         grp.close()
+
+
+@pytest.mark.gpu
+def test_window_falls_back_to_the_whole_source(tmp_path):
+    """GICPB_HALO_PLANES=0: the windows end where the shards end, so the kNN check must reject the neighbourhoods at the
+    edges, the source is indexed whole after all, and the answer is still the oracle's."""
+    import subprocess
+    import sys
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r})
+from leica_point_cloud_processing_b200 import EngineGroup, synth
+from oracle.oracle import Oracle, default_params
+orc = Oracle()
+s, t, _ = synth.make_pair(60_000, 60_000)
+grp = EngineGroup([0, 0])
+grp.set_params(max_corr_distance=1.0)
+grp.set_clouds(t, s)
+res = grp.align()
+ref = orc.align(s, t, default_params(max_corr_distance=1.0))
+info = [grp.member(r).shard_info() for r in range(2)]
+assert all(w >= 1 for _, _, _, w in info), info
+assert sum(hi - lo for lo, hi, _, _ in info) == len(s), info
+assert synth.rotation_error_rad(res["transform"], ref["T"]) <= 1e-4
+assert res["outer_iterations"] == ref["outer_iterations"]
+print("widened", info)
+"""
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, GICPB_HALO_PLANES="0"))
+    print(run.stdout[-2000:], run.stderr[-2000:])
+    assert run.returncode == 0
+    assert "widened" in run.stdout

@@ -64,7 +64,7 @@ def test_reference_gtests_pass_on_the_gpu(tmp_path, name, n_tests, devices):
     env = dict(os.environ, GICPB_STUB_PKG_PATH=str(tmp_path))
     if devices:
         env["GICPB_DEVICES"] = devices
-    run = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=env)
     print(run.stdout[-4000:], run.stderr[-3000:])
     assert run.returncode == 0
     assert "[  PASSED  ] %d tests." % n_tests in run.stdout
