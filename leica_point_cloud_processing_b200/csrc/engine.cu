@@ -232,6 +232,7 @@ struct gicpb_ctx {
   VoxelGrid voxel;
   DevBuf<int> uf_parent, uf_root;
   bool cov_ready = false;
+  bool tgt_normals_gathered = false;  // start_target_cov has already exchanged the target's normal chunks (second stream)
   int shard_lo = 0, shard_hi = 0;
   DevBuf<double> n_tgt, n_src;
   DevBuf<int> pair_pos;
@@ -405,6 +406,14 @@ void start_target_cov(gicpb_ctx* c, cudaStream_t knn_stream) {
   c->n_tgt.reserve(3 * (size_t)chunk * c->world);
   const FarWork fw = far_work(c, chunk);
   launch_knn_covariances(c->tgt.view(), t_lo, t_hi, k, c->n_tgt.get() + 3 * (size_t)t_lo, nullptr, nullptr, fw, knn_stream);
+  c->tgt_normals_gathered = false;
+  if (c->world > 1 && !c->local && knn_stream != c->stream) {
+    // gicpb_set_clouds: the chunks are exchanged on the second stream too, beside the source's index build (a chain of short
+    // kernels that leaves the links and most of the SMs idle), not in front of the source's covariance pass
+    check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
+                                     kNcclFloat64, c->comm, knn_stream), "ncclAllGather");
+    c->tgt_normals_gathered = true;
+  }
 }
 
 // the rest, on the context's stream (which must already be ordered after start_target_cov's kernels)
@@ -425,10 +434,11 @@ void finish_covariances(gicpb_ctx* c) {
       GICPB_CUDA(cudaMemcpyPeerAsync(c->n_tgt.get() + 3 * (size_t)r * chunk, c->device, o->n_tgt.get() + 3 * (size_t)r * chunk,
                                      o->device, 3 * (size_t)chunk * sizeof(double), c->stream));
     }
-  } else if (c->world > 1) {
+  } else if (c->world > 1 && !c->tgt_normals_gathered) {
     check_nccl(c, c->nccl->AllGather(c->n_tgt.get() + 3 * (size_t)c->rank * chunk, c->n_tgt.get(), 3 * (size_t)chunk,
                                      kNcclFloat64, c->comm, c->stream), "ncclAllGather");
   }
+  c->tgt_normals_gathered = false;
   const GridIndex::KnnWindow win = c->src.knn_window();
   unsigned* violations = c->far_counter.get() + 2;  // far_work() reserved 4 words; [0..1] belong to the far hand-over
   if (win.axis >= 0) {

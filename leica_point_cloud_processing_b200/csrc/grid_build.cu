@@ -622,11 +622,16 @@ void GridIndex::build(const void* raw, int64_t n, int64_t stride_bytes, bool on_
   win_.n_finite = n_valid;
   n_all_ = n;
   if (world > 1) {
-    int axis = 0;
-    if (bd[1] > bd[axis]) axis = 1;
-    if (bd[2] > bd[axis]) axis = 2;
+    // The planes are cut across the SECOND longest axis when it has enough of them, so that every rank owns a strip that
+    // runs the whole length of the cloud: the cost of a first correspondence pass grows with the distance from the centre
+    // of the misalignment, and slabs across the longest axis would give the ranks at the two ends all the expensive
+    // queries (measured on 8 GPUs, 8 M / 8 M: correspondence kernels of the slowest rank 4.5 ms against 2.9 ms).
+    int order[3] = {0, 1, 2};
+    std::sort(order, order + 3, [&](int a, int b) { return bd[a] != bd[b] ? bd[a] > bd[b] : a < b; });
+    auto usable = [&](int a) { return bd[a] >= 4 * world && bd[a] <= 8192; };
+    const int axis = usable(order[1]) ? order[1] : order[0];
     const int planes = bd[axis];
-    if (planes >= 4 * world && planes <= 8192 && n_valid >= 1024 * (int64_t)world) {
+    if (usable(axis) && n_valid >= 1024 * (int64_t)world) {
       const int o0 = axis == 0 ? 1 : 0, o1 = axis == 2 ? 1 : 2;  // the other two axes, in x < y < z order
       int strides[3];
       strides[o0] = 1;

@@ -15,6 +15,7 @@
 // distance); a query whose k-th neighbour is farther than that restarts on the hierarchical traversal (common.cuh).
 #include <atomic>
 #include <climits>
+#include <cstdlib>
 
 #include "kernels.hpp"
 #include "knn_search.cuh"
@@ -56,15 +57,14 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[9], double (&v)[9]) {
 
 constexpr int kKnnQueueCap = 12;
 
-template <bool kFar>
-__global__ void __launch_bounds__(kFar ? kKnnFarThreads : kKnnNearThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
+template <bool kFar, int kKnnThreads>
+__global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
                                                                double* __restrict__ normals,
                                                                int* __restrict__ knn_idx,
                                                                float* __restrict__ knn_d2, FarWork fw, int win_axis,
                                                                float win_lo, float win_hi,
                                                                unsigned* __restrict__ win_violations) {
   extern __shared__ __align__(8) int smem[];
-  constexpr int kKnnThreads = kFar ? kKnnFarThreads : kKnnNearThreads;
   KnnVisitor<kKnnThreads> L;
   L.pts = g.pts;
   L.lkey = reinterpret_cast<unsigned long long*>(smem) + threadIdx.x;
@@ -172,22 +172,32 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   const int n = hi - lo;
   if (n <= 0) return;
   reset_far(fw, n, stream);
-  const size_t heap_near = (size_t)2 * k * kKnnNearThreads * sizeof(int);
+  // threads per block of the near instance: 256 by default; GICPB_KNN_THREADS=128 for measurements
+  static const int near_threads = [] {
+    const char* e = std::getenv("GICPB_KNN_THREADS");
+    return (e && std::atoi(e) == 128) ? 128 : kKnnNearThreads;
+  }();
+  const size_t heap_near = (size_t)2 * k * near_threads * sizeof(int);
   const size_t heap = (size_t)2 * k * kKnnFarThreads * sizeof(int);
-  const size_t queue = (size_t)2 * kKnnQueueCap * kKnnNearThreads * sizeof(unsigned);
-  const unsigned nb = (unsigned)((n + kKnnNearThreads - 1) / kKnnNearThreads);
+  const size_t queue = (size_t)2 * kKnnQueueCap * near_threads * sizeof(unsigned);
+  const unsigned nb = (unsigned)((n + near_threads - 1) / near_threads);
   static std::atomic<unsigned long long> attr_set{0ull};  // one bit per device: the attribute belongs to the device's context
   int dev = 0;
   GICPB_CUDA(cudaGetDevice(&dev));
   if (dev >= 64 || !((attr_set.load() >> dev) & 1ull)) {  // up to 88 KB of dynamic shared memory at k = 32
-    GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     if (dev < 64) attr_set.fetch_or(1ull << dev);
   }
-  knn_cov_kernel<false><<<nb, kKnnNearThreads, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis,
-                                                                            win_lo, win_hi, win_violations);
+  if (near_threads == 128)
+    knn_cov_kernel<false, 128><<<nb, 128, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis, win_lo,
+                                                                      win_hi, win_violations);
+  else
+    knn_cov_kernel<false, 256><<<nb, 256, heap_near + queue, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis, win_lo,
+                                                                      win_hi, win_violations);
   GICPB_LAUNCHED();
-  knn_cov_kernel<true><<<fw.far_blocks, kKnnFarThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw, win_axis, win_lo,
-                                                                        win_hi, win_violations);
+  knn_cov_kernel<true, kKnnFarThreads><<<fw.far_blocks, kKnnFarThreads, heap, stream>>>(g, lo, hi, k, normals, knn_idx, knn_d2, fw,
+                                                                                       win_axis, win_lo, win_hi, win_violations);
   GICPB_LAUNCHED();
 }
 

@@ -130,7 +130,19 @@ __device__ __forceinline__ void onesweep_rank(const uint32_t (&key)[kOsItems], u
     const uint32_t d = (key[r] >> shift) & 255u;
     const unsigned active = kFull ? kFullMask : __ballot_sync(kFullMask, valid);
     rank[r] = 0;
-    if (valid) {
+    if (kFull) {
+      // the whole warp takes part: full-mask collectives (a shuffle under a computed mask costs a WARPSYNC / ENDCOLLECTIVE
+      // pair and a divergent branch per round)
+      const unsigned peers = __match_any_sync(kFullMask, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader) {
+        old = cnt_warp[d];
+        cnt_warp[d] = old + __popc(peers);
+      }
+      old = __shfl_sync(kFullMask, old, leader);
+      rank[r] = old + __popc(peers & lt);
+    } else if (valid) {
       const unsigned peers = __match_any_sync(active, d);
       const int leader = __ffs(peers) - 1;
       uint32_t old = 0;
