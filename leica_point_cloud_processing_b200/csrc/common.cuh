@@ -96,6 +96,7 @@ struct GridView {
   const unsigned long long* hb_mask;  // [nhx*nhy*nhz] occupancy of the 4x4x4 superbricks of a hyperbrick
   const float* brick_plane;      // [n_slots*5] or null: unit direction n of the brick's points (their PCA normal) and the
                                  // smallest / largest n.p over them: every point of the brick lies in that slab
+  const float* sb_plane;         // [nsx*nsy*nsz*5] or null: the same slab for all points of a superbrick (indexed like sb_mask)
   float ox, oy, oz;              // origin (min corner of cell (0,0,0))
   float h, inv_h;                // cell edge and its reciprocal
   float margin;                  // conservative slack (metres) for all box-distance lower bounds
@@ -159,12 +160,19 @@ GICPB_HD unsigned span4(int p, int r) {  // 4-bit mask of the coordinates in [p-
   const int lo = imax2(p - r, 0), hi = imin2(p + r, 3);
   return ((1u << (hi + 1)) - 1u) & ~((1u << lo) - 1u);
 }
-GICPB_HD unsigned long long box_mask64(int px, int py, int pz, int r) {
-  const unsigned xm = span4(px, r), ym = span4(py, r), zm = span4(pz, r);
+GICPB_HD unsigned long long spans_mask64(unsigned xm, unsigned ym, unsigned zm) {  // the box of three 4-bit coordinate sets
   const unsigned plane = xm * ((ym & 1u) | ((ym & 2u) << 3) | ((ym & 4u) << 6) | ((ym & 8u) << 9));
   const unsigned long long zs = (unsigned long long)(zm & 1u) | ((unsigned long long)(zm & 2u) << 15) |
                                 ((unsigned long long)(zm & 4u) << 30) | ((unsigned long long)(zm & 8u) << 45);
   return (unsigned long long)plane * zs;
+}
+GICPB_HD unsigned long long box_mask64(int px, int py, int pz, int r) {
+  return spans_mask64(span4(px, r), span4(py, r), span4(pz, r));
+}
+GICPB_HD unsigned range4(int lo, int hi) {  // 4-bit mask of the coordinates in [lo, hi] cut to [0,3]; 0 when empty
+  lo = imax2(lo, 0);
+  hi = imin2(hi, 3);
+  return lo > hi ? 0u : (((1u << (hi + 1)) - 1u) & ~((1u << lo) - 1u));
 }
 
 // ---- query context: the query point and its (clamped) cell ---------------------------------------------------------------
@@ -403,9 +411,37 @@ GICPB_HD bool visit_brick(const GridView& g, const Query& q, int bx, int by, int
 // the occupied children of one 4x4x4 mask, in Chebyshev rings around the child nearest to the query
 template <class V>
 GICPB_HD bool visit_superbrick(const GridView& g, const Query& q, int sx, int sy, int sz, V& v) {
-  const unsigned long long occ = ldg(&g.sb_mask[((size_t)sz * g.nsy + sy) * g.nsx + sx]);
+  const size_t sbi = ((size_t)sz * g.nsy + sy) * g.nsx + sx;
+  unsigned long long occ = ldg(&g.sb_mask[sbi]);
   if (!occ) return false;
   const float size = fmul(g.h, 8.0f);
+  if (g.sb_plane != nullptr && v.bound() < 3.0e38f) {
+    // Oriented slab of the whole superbrick (see visit_brick): a point p of it with |q - p|^2 <= bound lies, on every axis,
+    // within sqrt(bound - s^2) of the foot interval F_i.  Only the bricks that box touches are looked at: for a query far
+    // off a thin sheet that is the handful next to its foot instead of every brick the ball's own box covers.
+    const float* pl = g.sb_plane + 5 * sbi;
+    const float nx = ldg(&pl[0]), ny = ldg(&pl[1]), nz = ldg(&pl[2]), lo = ldg(&pl[3]), hi = ldg(&pl[4]);
+    const float nq = plane_dot(nx, ny, nz, q.x, q.y, q.z);
+    const float s = fmax2(fsub(fmax2(fsub(nq, hi), fsub(lo, nq)), g.margin), 0.f);
+    const float slab2 = fmul(fmul(s, s), 0.999998f);
+    const float bnd = v.bound();
+    if (slab2 > bnd) return false;
+    const float al = fsub(fsub(nq, hi), g.margin), ah = fadd(fsub(nq, lo), g.margin);  // alpha range, widened
+    const float x0 = fmul(nx, al), x1 = fmul(nx, ah), y0 = fmul(ny, al), y1 = fmul(ny, ah), z0 = fmul(nz, al), z1 = fmul(nz, ah);
+    const float rw = fadd(sqrt_up(fmax2(fsub(bnd, slab2), 0.f)), g.margin);
+    const float xl = fsub(fsub(q.x, fmax2(x0, x1)), rw), xh = fadd(fsub(q.x, fmin2(x0, x1)), rw);
+    const float yl = fsub(fsub(q.y, fmax2(y0, y1)), rw), yh = fadd(fsub(q.y, fmin2(y0, y1)), rw);
+    const float zl = fsub(fsub(q.z, fmax2(z0, z1)), rw), zh = fadd(fsub(q.z, fmin2(z0, z1)), rw);
+    // brick coordinates exactly as the build assigns them (clamped cells), relative to the superbrick
+    const unsigned xm = range4((clampi(cell_of(xl, g.ox, g.inv_h), 0, g.nx - 1) >> 3) - (sx << 2),
+                               (clampi(cell_of(xh, g.ox, g.inv_h), 0, g.nx - 1) >> 3) - (sx << 2));
+    const unsigned ym = range4((clampi(cell_of(yl, g.oy, g.inv_h), 0, g.ny - 1) >> 3) - (sy << 2),
+                               (clampi(cell_of(yh, g.oy, g.inv_h), 0, g.ny - 1) >> 3) - (sy << 2));
+    const unsigned zm = range4((clampi(cell_of(zl, g.oz, g.inv_h), 0, g.nz - 1) >> 3) - (sz << 2),
+                               (clampi(cell_of(zh, g.oz, g.inv_h), 0, g.nz - 1) >> 3) - (sz << 2));
+    occ &= spans_mask64(xm, ym, zm);
+    if (!occ) return false;
+  }
   const int px = clampi((q.cx >> 3) - (sx << 2), 0, 3), py = clampi((q.cy >> 3) - (sy << 2), 0, 3),
             pz = clampi((q.cz >> 3) - (sz << 2), 0, 3);
   unsigned long long seen = 0ull;

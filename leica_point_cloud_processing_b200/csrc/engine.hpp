@@ -151,6 +151,7 @@ class GridIndex {
   DevBuf<int> pos_of_;
   DevBuf<unsigned long long> sb_mask_, hb_mask_;
   DevBuf<float> brick_plane_;
+  DevBuf<float> sb_plane_;
   DevBuf<uint32_t> scratch_;  // bbox (6) + counters
   unsigned* h_pin_ = nullptr; // pinned host words the build reads its counters back into
   // sharded source (world > 1)

@@ -358,6 +358,15 @@ struct BuildTrace {
 
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// GICPB_SB_PLANE=0 leaves the superbrick slabs out of the view (measurements)
+inline bool use_sb_plane() {
+  static const bool on = [] {
+    const char* e = std::getenv("GICPB_SB_PLANE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace
 
 // Oriented slab of every occupied brick (GridView::brick_plane, used by visit_brick): one warp per brick slot.  The
@@ -439,6 +448,96 @@ __global__ void __launch_bounds__(128) brick_plane_kernel(const float4* __restri
   }
 }
 
+// The same slab for every occupied SUPERBRICK (GridView::sb_plane, used by visit_superbrick): one block per superbrick
+// walks the points of its occupied bricks twice (moments, then the extremes of plane_dot along the PCA normal).  Empty
+// superbricks get an empty slab; they are never looked at.
+__global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+                                                        const int* __restrict__ brick_slot, const unsigned long long* __restrict__ sb_mask,
+                                                        float* __restrict__ plane) {
+  __shared__ double s_sum[4][9];
+  __shared__ float s_lo[4], s_hi[4];
+  const int sb = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long occ = sb_mask[sb];
+  float* out = plane + 5 * (size_t)sb;
+  if (!occ) {
+    if (threadIdx.x == 0) { out[0] = 0.f; out[1] = 0.f; out[2] = 1.f; out[3] = __int_as_float(0x7f800000); out[4] = __int_as_float(0xff800000); }
+    return;
+  }
+  const int sx = sb % g.nsx, sy = (sb / g.nsx) % g.nsy, sz = sb / (g.nsx * g.nsy);
+  auto range_of = [&](int bit, unsigned& b, unsigned& e) {
+    const int bx = (sx << 2) + (bit & 3), by = (sy << 2) + ((bit >> 2) & 3), bz = (sz << 2) + (bit >> 4);
+    const int slot = brick_slot[brick_index(g, bx, by, bz)];
+    b = cell_start[(size_t)slot * kBrickCells];
+    e = cell_start[(size_t)(slot + 1) * kBrickCells];
+  };
+  unsigned b0, e0;
+  range_of(__ffsll((long long)occ) - 1, b0, e0);
+  const float4 p0 = pts[b0];  // moments about the first point (keeps the sums small), in double
+  double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
+  unsigned cnt = 0;
+  for (unsigned long long m = occ; m; m &= m - 1ull) {
+    unsigned b, e;
+    range_of(__ffsll((long long)m) - 1, b, e);
+    cnt += e - b;
+    for (unsigned i = b + threadIdx.x; i < e; i += 128) {
+      const float4 p = pts[i];
+      const double x = (double)p.x - (double)p0.x, y = (double)p.y - (double)p0.y, z = (double)p.z - (double)p0.z;
+      sm[0] += x; sm[1] += y; sm[2] += z;
+      sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    sm[k] = warp_sum(sm[k]);
+    if (lane == 0) s_sum[warp][k] = sm[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 9; ++k) sm[k] = ((s_sum[0][k] + s_sum[1][k]) + s_sum[2][k]) + s_sum[3][k];  // the same value in every thread
+  const double m = (double)cnt;
+  const double mx = sm[0] / m, my = sm[1] / m, mz = sm[2] / m;
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  a[0] = sm[3] / m - mx * mx; a[1] = sm[4] / m - mx * my; a[2] = sm[5] / m - mx * mz;
+  a[4] = sm[6] / m - my * my; a[5] = sm[7] / m - my * mz; a[8] = sm[8] / m - mz * mz;
+  a[3] = a[1]; a[6] = a[2]; a[7] = a[5];
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    const double off = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
+    if (off == 0.0 || off < 1e-20 * (fabs(a[0]) + fabs(a[4]) + fabs(a[8]))) break;
+    jacobi3(a, v, 0, 1);
+    jacobi3(a, v, 0, 2);
+    jacobi3(a, v, 1, 2);
+  }
+  int best = 0;
+  if (fabs(a[4]) < fabs(a[0])) best = 1;
+  if (fabs(a[8]) < fabs(a[4 * best])) best = 2;
+  float nx = (float)v[best], ny = (float)v[3 + best], nz = (float)v[6 + best];
+  if (!(fabsf(nx) + fabsf(ny) + fabsf(nz) > 0.5f)) { nx = 0.f; ny = 0.f; nz = 1.f; }
+  float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+  for (unsigned long long mm = occ; mm; mm &= mm - 1ull) {
+    unsigned b, e;
+    range_of(__ffsll((long long)mm) - 1, b, e);
+    for (unsigned i = b + threadIdx.x; i < e; i += 128) {
+      const float4 p = pts[i];
+      const float d = plane_dot(nx, ny, nz, p.x, p.y, p.z);
+      lo = fminf(lo, d);
+      hi = fmaxf(hi, d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(kFullMask, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(kFullMask, hi, o));
+  }
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[0] = nx; out[1] = ny; out[2] = nz;
+    out[3] = fminf(fminf(s_lo[0], s_lo[1]), fminf(s_lo[2], s_lo[3]));
+    out[4] = fmaxf(fmaxf(s_hi[0], s_hi[1]), fmaxf(s_hi[2], s_hi[3]));
+  }
+}
+
 // Ask for the largest shared-memory carve-out on every index-build kernel so that their blocks can share an SM with the
 // kNN kernel (which needs it) when both run on different streams (gicpb_set_clouds).
 void prefer_shared_carveout_grid() {
@@ -456,6 +555,7 @@ void prefer_shared_carveout_grid() {
   cudaFuncSetAttribute(cell_heads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(cell_fill_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   cudaFuncSetAttribute(brick_plane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(sb_plane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   (void)cudaGetLastError();
 }
 
@@ -812,12 +912,20 @@ void GridIndex::index_points(const float4* pts, int64_t n, int64_t n_valid, cons
   brick_plane_kernel<<<blocks_for(n_slots * 32, 128), 128, 0, stream>>>(pts_sorted_.get(), cell_start_.get(), (int)n_slots,
                                                                         brick_plane_.get());
   GICPB_LAUNCHED();
+  sb_plane_.reserve(n_sb * 5);
+  {
+    GridView gv = g;  // the kernel needs the geometry and the brick numbering only
+    sb_plane_kernel<<<(unsigned)n_sb, 128, 0, stream>>>(gv, pts_sorted_.get(), cell_start_.get(), brick_slot_.get(), sb_mask_.get(),
+                                                       sb_plane_.get());
+    GICPB_LAUNCHED();
+  }
   trace.mark("plane");
   GICPB_CUDA(cudaMemcpyAsync(hs, scratch_.get(), kHsBytes, cudaMemcpyDeviceToHost, stream));
   GICPB_CUDA(cudaStreamSynchronize(stream));
 
   g.pts = pts_sorted_.get();
   g.brick_plane = brick_plane_.get();
+  g.sb_plane = use_sb_plane() ? sb_plane_.get() : nullptr;
   g.brick_slot = brick_slot_.get();
   g.cell_start = cell_start_.get();
   g.pos_of = pos_of_.get();

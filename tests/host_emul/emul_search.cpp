@@ -22,7 +22,7 @@ struct HostIndex {
   std::vector<uint32_t> cell_start;
   std::vector<unsigned long long> sb, hb;
   std::vector<int> pos_of;
-  std::vector<float> plane;
+  std::vector<float> plane, sb_plane;
   GridView g{};
 };
 
@@ -151,6 +151,34 @@ static void build_index(const std::vector<float3>& in, float h, HostIndex& ix) {
     pl[3] = std::min(pl[3], d); pl[4] = std::max(pl[4], d);
   }
   g.brick_plane = ix.plane.data();
+  // the same slab per SUPERBRICK (sb_plane_kernel): the direction of the superbrick's first occupied brick (for a sheet
+  // that is close to the superbrick's own PCA normal; every third superbrick keeps an arbitrary direction: any unit
+  // vector must leave the search exact), extremes of plane_dot over all points of the superbrick
+  const size_t n_sb = (size_t)g.nsx * g.nsy * g.nsz;
+  ix.sb_plane.assign(n_sb * 5, 0.f);
+  for (size_t b = 0; b < n_sb; ++b) { float* pl = &ix.sb_plane[b * 5]; pl[2] = 1.f; pl[3] = inf(); pl[4] = -inf(); }
+  std::vector<char> sb_has(n_sb, 0);
+  auto sb_of = [&](int i) {
+    const int b = (int)(kv[i].first >> 9);
+    const int bx = b % g.nbx, by = (b / g.nbx) % g.nby, bz = b / (g.nbx * g.nby);
+    return ((size_t)(bz >> 2) * g.nsy + (by >> 2)) * g.nsx + (bx >> 2);
+  };
+  for (int i = 0; i < n; ++i) {
+    const size_t b = sb_of(i);
+    if (sb_has[b]) continue;
+    sb_has[b] = 1;
+    float* pl = &ix.sb_plane[b * 5];
+    const float* bp = &ix.plane[(size_t)slot_of[i] * 5];
+    pl[0] = bp[0]; pl[1] = bp[1]; pl[2] = bp[2];
+    if (b % 3 == 2) { pl[0] = -0.36f; pl[1] = 0.8f; pl[2] = 0.48f; }
+  }
+  for (int i = 0; i < n; ++i) {
+    float* pl = &ix.sb_plane[sb_of(i) * 5];
+    const float4& p = ix.pts[i];
+    const float d = plane_dot(pl[0], pl[1], pl[2], p.x, p.y, p.z);
+    pl[3] = std::min(pl[3], d); pl[4] = std::max(pl[4], d);
+  }
+  g.sb_plane = ix.sb_plane.data();
 }
 
 static long g_fail = 0, g_checks = 0, g_far = 0, g_knn_far = 0;
