@@ -146,7 +146,6 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
   __shared__ double sm[kWarps][kCostSums + 2];
   __shared__ double red[kThreads / 16][16];
   __shared__ bool is_last;
-  __shared__ int timed_out;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < kCostSums; ++c) {
@@ -193,42 +192,48 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
     return;
   }
   // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
+  // Every sum travels as two self-validating 8-byte messages (32 bits of the double | the evaluation counter): an aligned
+  // 8-byte store is single-copy atomic, so a word that shows `seq` shows this evaluation's payload - no fence between
+  // payload and flag, no separate flag, one NVLink crossing per evaluation instead of two plus two system-wide fences.
+  __shared__ double s_own[kCostSums];
+  __shared__ unsigned s_rx[kMaxPeers][2 * kCostSums];
+  __shared__ int timed_out;
   const int set = (int)(pr.seq & 1u);
-  if (threadIdx.x < kCostSums)
-    for (int p = 0; p < pr.world; ++p) {
-      volatile double* dst = &pr.peers[p]->vals[set][pr.rank][threadIdx.x];
-      *dst = s;
-    }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < pr.world) {
-    volatile unsigned* f = &pr.peers[threadIdx.x]->flag[set][pr.rank];
-    *f = pr.seq;  // thread p tells rank p that this rank's sums of evaluation `seq` are in place
-  }
+  if (threadIdx.x < kCostSums) s_own[threadIdx.x] = s;
   if (threadIdx.x == 0) timed_out = 0;
   __syncthreads();
-  if (threadIdx.x < pr.world) {
-    volatile unsigned* f = &pr.peers[pr.rank]->flag[set][threadIdx.x];
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (threadIdx.x < 2 * kCostSums) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(s_own[threadIdx.x >> 1]);
+    const unsigned half = (threadIdx.x & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+    const unsigned long long msg = ((unsigned long long)half << 32) | (unsigned long long)pr.seq;
+    for (int p = 0; p < pr.world; ++p) {
+      volatile unsigned long long* dst = &pr.peers[p]->msg[set][pr.rank][threadIdx.x];
+      *dst = msg;
+    }
+  }
+  for (int idx = threadIdx.x; idx < pr.world * 32; idx += kThreads) {
+    const int r = idx >> 5, j = idx & 31;
+    if (j >= 2 * kCostSums) continue;
+    volatile unsigned long long* src_w = &pr.peers[pr.rank]->msg[set][r][j];
+    unsigned long long t0 = 0, t1, w;
     unsigned spins = 0;
-    while (*f != pr.seq) {
+    while ((unsigned)((w = *src_w) & 0xffffffffull) != pr.seq) {
       if ((++spins & 0xffu) != 0u) continue;
+      if (t0 == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > pr.timeout_ns) {  // wall-clock nanoseconds (not SM cycles): a peer never launched this evaluation
         timed_out = 1;
         break;
       }
     }
+    s_rx[r][j] = (unsigned)(w >> 32);
   }
   __syncthreads();
-  __threadfence_system();
   if (threadIdx.x < kCostSums) {
     double t = 0.0;
-    for (int r = 0; r < pr.world; ++r) {
-      volatile double* pv = &pr.peers[pr.rank]->vals[set][r][threadIdx.x];
-      t += *pv;
-    }
+    for (int r = 0; r < pr.world; ++r)  // rank order: the same sum, bit for bit, on every rank
+      t += __longlong_as_double((long long)(((unsigned long long)s_rx[r][2 * threadIdx.x + 1] << 32) |
+                                            (unsigned long long)s_rx[r][2 * threadIdx.x]));
     out[threadIdx.x] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
   }
   if (stamp) {
