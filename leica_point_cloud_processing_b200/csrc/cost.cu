@@ -136,7 +136,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // ---- block / grid reduction of the 14 sums and their publication (shared by the per-launch and the persistent kernel) ----
 // Warp shuffles -> shared-memory block tree -> per-block row of `partials` -> the last block to arrive (ticket) adds the
 // rows in a fixed order (a given input always produces the same bits) and writes `out`.  stamp != 0: `out` is mapped host
-// memory the host polls; out[15] = stamp is stored after the 14 sums are visible system-wide.  kPeer: the sums are first
+// memory the host polls: the sums travel as stamped 8-byte words (kernels.hpp launch_cost).  kPeer: the sums are first
 // exchanged with the other ranks through peer memory (kernels.hpp PeerReduce).  Must be called by every thread of the block.
 template <int kThreads, bool kPeer>
 __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums], double* __restrict__ partials,
@@ -182,20 +182,32 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
     for (int gi = 0; gi < kThreads / 16; ++gi) s += red[gi][threadIdx.x];
   }
   if (threadIdx.x == 0) *ticket = 0u;
-  if (!kPeer) {
-    if (threadIdx.x < kCostSums) out[threadIdx.x] = s;
-    if (stamp) {
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
+  __shared__ double s_own[kCostSums];
+  // stamp != 0: the result goes to the polling host as 28 self-validating 8-byte words (32 bits of a sum | stamp) behind the
+  // 16 plain doubles of `out` (kCostOutWords): no fence and no separate flag between the sums and their "ready" mark
+  auto publish = [&](bool have) {  // s_own holds the 14 results (written by the threads < kCostSums before a barrier)
+    if (!have) return;
+    if (threadIdx.x < 2 * kCostSums) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(s_own[threadIdx.x >> 1]);
+      const unsigned half = (threadIdx.x & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
+      volatile unsigned long long* w = reinterpret_cast<volatile unsigned long long*>(out + kCostOutWords) + threadIdx.x;
+      *w = ((unsigned long long)half << 32) | (unsigned long long)stamp;
     }
+  };
+  if (!kPeer) {
+    if (!stamp) {
+      if (threadIdx.x < kCostSums) out[threadIdx.x] = s;
+      return;
+    }
+    if (threadIdx.x < kCostSums) s_own[threadIdx.x] = s;
+    __syncthreads();
+    publish(true);
     return;
   }
   // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
   // Every sum travels as two self-validating 8-byte messages (32 bits of the double | the evaluation counter): an aligned
   // 8-byte store is single-copy atomic, so a word that shows `seq` shows this evaluation's payload - no fence between
   // payload and flag, no separate flag, one NVLink crossing per evaluation instead of two plus two system-wide fences.
-  __shared__ double s_own[kCostSums];
   __shared__ unsigned s_rx[kMaxPeers][2 * kCostSums];
   __shared__ int timed_out;
   const int set = (int)(pr.seq & 1u);
@@ -234,12 +246,15 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
     for (int r = 0; r < pr.world; ++r)  // rank order: the same sum, bit for bit, on every rank
       t += __longlong_as_double((long long)(((unsigned long long)s_rx[r][2 * threadIdx.x + 1] << 32) |
                                             (unsigned long long)s_rx[r][2 * threadIdx.x]));
-    out[threadIdx.x] = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
+    t = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : t;
+    if (stamp)
+      s_own[threadIdx.x] = t;  // every thread has read s_own (its own sums) before the barrier above
+    else
+      out[threadIdx.x] = t;
   }
   if (stamp) {
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile double*>(out + 15) = (double)stamp;
+    publish(true);
   }
 }
 

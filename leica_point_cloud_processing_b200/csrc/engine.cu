@@ -643,7 +643,8 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
   if (polled) {
     if (++c->eval_stamp == 0u || c->eval_stamp >= (1u << 30)) {
       c->eval_stamp = 1u;
-      c->h_sums[15] = 0.0;  // no kernel is in flight here (every evaluation is waited for): forget the pre-wrap stamps
+      // no kernel is in flight here (every evaluation is waited for): forget the pre-wrap stamps
+      std::memset(c->h_sums + kCostOutWords, 0, 32 * sizeof(unsigned long long));
     }
     stamp = c->eval_stamp;
   }
@@ -659,14 +660,24 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
     launch_cost(c->src.sorted_points(), c->shard_lo, n, c->pair_tgt.get(), c->maha.get(), c->pairs_fp32, T,
                 c->partials.get(), c->ticket.get(), out, blocks, c->stream, fused ? &c->peer : nullptr, stamp);
   if (polled) {
-    const volatile double* flag = c->h_sums + 15;
-    const double want = (double)stamp;
+    // 28 self-validating words (kernels.hpp launch_cost): every one must show this evaluation's stamp
+    const volatile unsigned long long* words = reinterpret_cast<const volatile unsigned long long*>(c->h_sums + kCostOutWords);
+    unsigned long long got[2 * kCostSums];
+    int have = 0;  // words [0, have) have arrived
+    auto arrived = [&] {
+      while (have < 2 * kCostSums) {
+        const unsigned long long w = words[have];
+        if ((unsigned)(w & 0xffffffffull) != stamp) return false;
+        got[have++] = w;
+      }
+      return true;
+    };
     int relaunches = 0;
-    for (unsigned spins = 1; *flag != want; ++spins) {
+    for (unsigned spins = 1; !arrived(); ++spins) {
       if ((spins & 0x3fffu) == 0u) {  // every ~16 k polls: has the kernel died, or finished without publishing?
         const cudaError_t q = cudaStreamQuery(c->stream);
         if (q == cudaSuccess) {
-          if (*flag == want) break;
+          if (arrived()) break;
           if (session && relaunches < 3) {
             // the resident kernel ended itself (no command for cost_idle_ns: this thread was descheduled) before it saw
             // the command: launch it again and repeat the command
@@ -681,7 +692,10 @@ void run_cost(gicpb_ctx* c, const double* x, double* sums) {
         (void)cudaGetLastError();
       }
     }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int i = 0; i < kCostSums; ++i) {
+      const unsigned long long bits = (got[2 * i + 1] & 0xffffffff00000000ull) | (got[2 * i] >> 32);
+      std::memcpy(&c->h_sums[i], &bits, sizeof(double));
+    }
   } else {
     all_reduce_sum(c, c->d_sums.get(), kCostSums);
     GICPB_CUDA(cudaMemcpyAsync(c->h_sums, c->d_sums.get(), kCostSums * sizeof(double), cudaMemcpyDeviceToHost,
@@ -1128,9 +1142,9 @@ int gicpb_create(int device, gicpb_ctx** out) {
     GICPB_CUDA(cudaEventCreate(&c->ev1));
     GICPB_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
     for (auto& p : c->prefetch) GICPB_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
-    GICPB_CUDA(cudaHostAlloc(&c->h_sums, 16 * sizeof(double), cudaHostAllocMapped));
+    GICPB_CUDA(cudaHostAlloc(&c->h_sums, kCostOutDoubles * sizeof(double), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_sums_dev, c->h_sums, 0));
-    std::memset(c->h_sums, 0, 16 * sizeof(double));  // h_sums[15] is polled for a stamp: recycled pinned pages may hold one
+    std::memset(c->h_sums, 0, kCostOutDoubles * sizeof(double));  // the result words are polled for a stamp: recycled pinned pages may hold one
     GICPB_CUDA(cudaHostAlloc(&c->h_cmd, 2 * sizeof(CostCommand), cudaHostAllocMapped));
     GICPB_CUDA(cudaHostGetDevicePointer(&c->h_cmd_dev, c->h_cmd, 0));
     std::memset(c->h_cmd, 0, 2 * sizeof(CostCommand));

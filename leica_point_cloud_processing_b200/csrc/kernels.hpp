@@ -151,12 +151,16 @@ struct PeerReduce {
 void launch_cost(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                  const Rigid& T, double* partials, unsigned* ticket, double* out14, int blocks, cudaStream_t stream,
                  const PeerReduce* peer = nullptr, unsigned stamp = 0);
-// stamp != 0: out14 must be mapped host memory of 16 doubles; the kernel stores (double)stamp into out14[15] once the 14
-// sums are visible to the host, which can then poll that word instead of synchronising the stream.
+// stamp != 0 (below 2^32, never 0): out14 must be mapped host memory of kCostOutDoubles doubles; the kernel then sends
+// the 14 sums as 28 self-validating 8-byte words - (32 bits of sum j / 2, low half first) << 32 | stamp - at
+// out14 + kCostOutWords, which the host polls instead of synchronising the stream: a word that shows the stamp shows its
+// payload (aligned 8-byte stores are single-copy atomic), so the kernel needs no system-wide fence before a "ready" flag.
+constexpr int kCostOutWords = 32;    // offset (in doubles) of the 32 result words behind the 16 plain doubles
+constexpr int kCostOutDoubles = 64;
 
 // Persistent evaluation kernel (cost.cu cost_persistent_kernel): launched once per outer iteration, one block per SM; every
 // evaluation is a CostCommand the host writes into mapped pinned memory (seq LAST) and the kernel answers through the
-// stamp in out16[15].  seq = (epoch << 20) | k for the k-th command (k = 1, 2, ...) of the launch with that epoch.
+// stamped result words behind out16 (launch_cost).  seq = (epoch << 20) | k for the k-th command (k = 1, 2, ...) of the launch with that epoch.
 constexpr unsigned kCostOpEval = 1u, kCostOpExit = 2u;
 // A command is five self-validating 16-byte chunks: each carries the sequence word in its last lane, and the host writes
 // a chunk's payload before its sequence word.  A 16-byte read (one PCIe read inside one cache line, or one L2 access)
@@ -173,7 +177,7 @@ static_assert(sizeof(CostCommand) == 128, "CostCommand layout");
 int cost_persistent_blocks(int num_sms);
 // hcmd_dev: device alias of the mapped host command slot of this launch (the host alternates between two slots by epoch,
 // so the EXIT of one launch is never overwritten by the first command of the next); dcmd: one CostCommand in device memory; partials / ticket as
-// launch_cost (blocks rows); out16: mapped host memory of 16 doubles; smem_optin: cudaDevAttrMaxSharedMemoryPerBlockOptin.
+// launch_cost (blocks rows); out16: mapped host memory of kCostOutDoubles doubles; smem_optin: cudaDevAttrMaxSharedMemoryPerBlockOptin.
 void launch_cost_persistent(const float4* src, int lo, int n, const float4* pair_tgt, const void* maha, bool maha_fp32,
                             const CostCommand* hcmd_dev, CostCommand* dcmd, unsigned epoch, double* partials, unsigned* ticket,
                             double* out16, const PeerReduce* peer, unsigned long long idle_timeout_ns, int blocks,
