@@ -1137,6 +1137,7 @@ int gicpb_create(int device, gicpb_ctx** out) {
       prefer_shared_carveout_grid();
       prefer_shared_carveout_sort();
     }
+    c->src.expect_far_queries(false);  // the source is searched from its own points only (kNN, resolution, normals)
     GICPB_CUDA(cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming));
     GICPB_CUDA(cudaEventCreate(&c->ev0));
     GICPB_CUDA(cudaEventCreate(&c->ev1));

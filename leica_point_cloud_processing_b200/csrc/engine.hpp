@@ -129,6 +129,9 @@ class GridIndex {
   int64_t n_points() const { return info_.n_points; }
   const float4* sorted_points() const { return pts_sorted_.get(); }
   void reset() { ready_ = false; }
+  // false: a cloud that is only ever searched from its own points (the source of a registration job: kNN) - the superbrick
+  // slabs, which pay off for queries far off the cloud, are then not built
+  void expect_far_queries(bool yes) { far_queries_ = yes; }
   // device staging buffer for a host cloud that the caller uploads itself (prefetch on another stream)
   unsigned char* stage(size_t bytes) {
     raw_.reserve(bytes);
@@ -137,6 +140,7 @@ class GridIndex {
 
  private:
   bool ready_ = false;
+  bool far_queries_ = true;
   GridView view_{};
   Info info_{};
   DevBuf<unsigned char> raw_;

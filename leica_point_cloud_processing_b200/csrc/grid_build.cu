@@ -451,11 +451,14 @@ __global__ void __launch_bounds__(128) brick_plane_kernel(const float4* __restri
 // The same slab for every occupied SUPERBRICK (GridView::sb_plane, used by visit_superbrick): one block per superbrick
 // walks the points of its occupied bricks twice (moments, then the extremes of plane_dot along the PCA normal).  Empty
 // superbricks get an empty slab; they are never looked at.
-__global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
-                                                        const int* __restrict__ brick_slot, const unsigned long long* __restrict__ sb_mask,
-                                                        float* __restrict__ plane) {
-  __shared__ double s_sum[4][9];
-  __shared__ float s_lo[4], s_hi[4];
+constexpr int kSbThreads = 512;
+__global__ void __launch_bounds__(kSbThreads) sb_plane_kernel(GridView g, const float4* __restrict__ pts, const uint32_t* __restrict__ cell_start,
+                                                               const int* __restrict__ brick_slot, const unsigned long long* __restrict__ sb_mask,
+                                                               float* __restrict__ plane) {
+  constexpr int kWarps = kSbThreads / 32;
+  __shared__ unsigned s_b[64], s_pre[65];
+  __shared__ double s_sum[kWarps][9];
+  __shared__ float s_lo[kWarps], s_hi[kWarps];
   const int sb = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long occ = sb_mask[sb];
@@ -464,28 +467,48 @@ __global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4*
     if (threadIdx.x == 0) { out[0] = 0.f; out[1] = 0.f; out[2] = 1.f; out[3] = __int_as_float(0x7f800000); out[4] = __int_as_float(0xff800000); }
     return;
   }
-  const int sx = sb % g.nsx, sy = (sb / g.nsx) % g.nsy, sz = sb / (g.nsx * g.nsy);
-  auto range_of = [&](int bit, unsigned& b, unsigned& e) {
-    const int bx = (sx << 2) + (bit & 3), by = (sy << 2) + ((bit >> 2) & 3), bz = (sz << 2) + (bit >> 4);
-    const int slot = brick_slot[brick_index(g, bx, by, bz)];
-    b = cell_start[(size_t)slot * kBrickCells];
-    e = cell_start[(size_t)(slot + 1) * kBrickCells];
-  };
-  unsigned b0, e0;
-  range_of(__ffsll((long long)occ) - 1, b0, e0);
-  const float4 p0 = pts[b0];  // moments about the first point (keeps the sums small), in double
-  double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
-  unsigned cnt = 0;
-  for (unsigned long long m = occ; m; m &= m - 1ull) {
-    unsigned b, e;
-    range_of(__ffsll((long long)m) - 1, b, e);
-    cnt += e - b;
-    for (unsigned i = b + threadIdx.x; i < e; i += 128) {
-      const float4 p = pts[i];
-      const double x = (double)p.x - (double)p0.x, y = (double)p.y - (double)p0.y, z = (double)p.z - (double)p0.z;
-      sm[0] += x; sm[1] += y; sm[2] += z;
-      sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
+  // the point ranges of the occupied bricks, all looked up at once, then ONE flat loop over the superbrick's points
+  if (threadIdx.x < 64) {
+    unsigned b = 0, e = 0;
+    if ((occ >> threadIdx.x) & 1ull) {
+      const int sx = sb % g.nsx, sy = (sb / g.nsx) % g.nsy, sz = sb / (g.nsx * g.nsy);
+      const int bit = threadIdx.x;
+      const int bx = (sx << 2) + (bit & 3), by = (sy << 2) + ((bit >> 2) & 3), bz = (sz << 2) + (bit >> 4);
+      const int slot = brick_slot[brick_index(g, bx, by, bz)];
+      b = cell_start[(size_t)slot * kBrickCells];
+      e = cell_start[(size_t)(slot + 1) * kBrickCells];
     }
+    s_b[threadIdx.x] = b;
+    // inclusive scan of the 64 lengths over two warps
+    unsigned incl = e - b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_up_sync(kFullMask, incl, o);
+      if (lane >= o) incl += v;
+    }
+    s_pre[threadIdx.x + 1] = incl;
+  }
+  if (threadIdx.x == 0) s_pre[0] = 0u;
+  __syncthreads();
+  const unsigned first_half = s_pre[32];
+  __syncthreads();
+  if (threadIdx.x >= 32 && threadIdx.x < 64) s_pre[threadIdx.x + 1] += first_half;
+  __syncthreads();
+  const unsigned total = s_pre[64];
+  auto point_at = [&](unsigned f) {  // f-th point of the superbrick: the last brick whose prefix is <= f
+    int j = 0;
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1)
+      if (s_pre[j + step] <= f) j += step;
+    return s_b[j] + (f - s_pre[j]);
+  };
+  const float4 p0 = pts[point_at(0u)];  // moments about the first point (keeps the sums small), in double
+  double sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // x y z xx xy xz yy yz zz
+  for (unsigned f = threadIdx.x; f < total; f += kSbThreads) {
+    const float4 p = pts[point_at(f)];
+    const double x = (double)p.x - (double)p0.x, y = (double)p.y - (double)p0.y, z = (double)p.z - (double)p0.z;
+    sm[0] += x; sm[1] += y; sm[2] += z;
+    sm[3] += x * x; sm[4] += x * y; sm[5] += x * z; sm[6] += y * y; sm[7] += y * z; sm[8] += z * z;
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -494,8 +517,13 @@ __global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4*
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < 9; ++k) sm[k] = ((s_sum[0][k] + s_sum[1][k]) + s_sum[2][k]) + s_sum[3][k];  // the same value in every thread
-  const double m = (double)cnt;
+  for (int k = 0; k < 9; ++k) {  // the same value in every thread
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s_sum[w][k];
+    sm[k] = t;
+  }
+  const double m = (double)total;
   const double mx = sm[0] / m, my = sm[1] / m, mz = sm[2] / m;
   double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   a[0] = sm[3] / m - mx * mx; a[1] = sm[4] / m - mx * my; a[2] = sm[5] / m - mx * mz;
@@ -514,15 +542,11 @@ __global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4*
   float nx = (float)v[best], ny = (float)v[3 + best], nz = (float)v[6 + best];
   if (!(fabsf(nx) + fabsf(ny) + fabsf(nz) > 0.5f)) { nx = 0.f; ny = 0.f; nz = 1.f; }
   float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
-  for (unsigned long long mm = occ; mm; mm &= mm - 1ull) {
-    unsigned b, e;
-    range_of(__ffsll((long long)mm) - 1, b, e);
-    for (unsigned i = b + threadIdx.x; i < e; i += 128) {
-      const float4 p = pts[i];
-      const float d = plane_dot(nx, ny, nz, p.x, p.y, p.z);
-      lo = fminf(lo, d);
-      hi = fmaxf(hi, d);
-    }
+  for (unsigned f = threadIdx.x; f < total; f += kSbThreads) {
+    const float4 p = pts[point_at(f)];
+    const float d = plane_dot(nx, ny, nz, p.x, p.y, p.z);
+    lo = fminf(lo, d);
+    hi = fmaxf(hi, d);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -532,9 +556,10 @@ __global__ void __launch_bounds__(128) sb_plane_kernel(GridView g, const float4*
   if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
   __syncthreads();
   if (threadIdx.x == 0) {
+    for (int w = 1; w < kWarps; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
     out[0] = nx; out[1] = ny; out[2] = nz;
-    out[3] = fminf(fminf(s_lo[0], s_lo[1]), fminf(s_lo[2], s_lo[3]));
-    out[4] = fmaxf(fmaxf(s_hi[0], s_hi[1]), fmaxf(s_hi[2], s_hi[3]));
+    out[3] = lo;
+    out[4] = hi;
   }
 }
 
@@ -912,10 +937,10 @@ void GridIndex::index_points(const float4* pts, int64_t n, int64_t n_valid, cons
   brick_plane_kernel<<<blocks_for(n_slots * 32, 128), 128, 0, stream>>>(pts_sorted_.get(), cell_start_.get(), (int)n_slots,
                                                                         brick_plane_.get());
   GICPB_LAUNCHED();
-  sb_plane_.reserve(n_sb * 5);
-  {
+  if (far_queries_ && use_sb_plane()) {
+    sb_plane_.reserve(n_sb * 5);
     GridView gv = g;  // the kernel needs the geometry and the brick numbering only
-    sb_plane_kernel<<<(unsigned)n_sb, 128, 0, stream>>>(gv, pts_sorted_.get(), cell_start_.get(), brick_slot_.get(), sb_mask_.get(),
+    sb_plane_kernel<<<(unsigned)n_sb, kSbThreads, 0, stream>>>(gv, pts_sorted_.get(), cell_start_.get(), brick_slot_.get(), sb_mask_.get(),
                                                        sb_plane_.get());
     GICPB_LAUNCHED();
   }
@@ -925,7 +950,7 @@ void GridIndex::index_points(const float4* pts, int64_t n, int64_t n_valid, cons
 
   g.pts = pts_sorted_.get();
   g.brick_plane = brick_plane_.get();
-  g.sb_plane = use_sb_plane() ? sb_plane_.get() : nullptr;
+  g.sb_plane = (far_queries_ && use_sb_plane()) ? sb_plane_.get() : nullptr;
   g.brick_slot = brick_slot_.get();
   g.cell_start = cell_start_.get();
   g.pos_of = pos_of_.get();

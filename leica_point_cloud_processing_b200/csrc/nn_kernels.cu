@@ -213,10 +213,23 @@ __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridV
     }
   };
   GICPB_RUN_ITEMS(hi - lo, body)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (!kFar) {
+    // near instance: one row per WARP and no block-wide barrier - a warp whose queries are done leaves instead of holding
+    // its place on the SM until the slowest warp of the block arrives (the barrier was 30 % of this kernel's stall samples)
+    __syncwarp();
+    sum = warp_sum(sum);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+      const size_t row = (size_t)row0 + (size_t)blockIdx.x * (kNnThreads / 32) + warp;
+      partials[2 * row] = sum;
+      partials[2 * row + 1] = cnt;
+    }
+    return;
+  }
   __syncthreads();
   sum = warp_sum(sum);
   cnt = warp_sum(cnt);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     ssum[warp] = sum;
     scnt[warp] = cnt;
@@ -228,19 +241,29 @@ __global__ void __launch_bounds__(kNnThreads, kFar ? 6 : 8) fitness_kernel(GridV
   }
 }
 
-// out[c] = sum over rows of partials[row*ncols + c], fixed order (deterministic)
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ partials, int nrows, int ncols,
-                                                               double* __restrict__ out) {
-  __shared__ double sm[8];
+// out[c] = sum over rows of partials[row*ncols + c], fixed order (deterministic): one block of 1024 threads, four
+// independent partial sums per thread (rows t, t + 1024, ... taken four at a time) so that the loads are all in flight
+constexpr int kReduceThreads = 1024;
+__global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const double* __restrict__ partials, int nrows, int ncols,
+                                                                          double* __restrict__ out) {
+  __shared__ double sm[kReduceThreads / 32];
   for (int c = 0; c < ncols; ++c) {
-    double v = 0.0;
-    for (int r = threadIdx.x; r < nrows; r += blockDim.x) v += partials[(size_t)r * ncols + c];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = threadIdx.x;
+    for (; r + 3 * kReduceThreads < nrows; r += 4 * kReduceThreads) {
+      a0 += partials[(size_t)r * ncols + c];
+      a1 += partials[(size_t)(r + kReduceThreads) * ncols + c];
+      a2 += partials[(size_t)(r + 2 * kReduceThreads) * ncols + c];
+      a3 += partials[(size_t)(r + 3 * kReduceThreads) * ncols + c];
+    }
+    for (; r < nrows; r += kReduceThreads) a0 += partials[(size_t)r * ncols + c];
+    double v = (a0 + a1) + (a2 + a3);
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
     if (threadIdx.x == 0) {
       double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += sm[w];
+      for (int w = 0; w < kReduceThreads / 32; ++w) t += sm[w];
       out[c] = t;
     }
     __syncthreads();
@@ -411,7 +434,8 @@ void launch_correspondences(const GridView& g, const float4* src, int lo, int hi
   }
 }
 
-int fitness_partial_rows(int n, int far_blocks) { return (int)nblocks(n, kNnThreads) + far_blocks; }
+// near instance: one row per warp; far instance: one row per block
+int fitness_partial_rows(int n, int far_blocks) { return (int)nblocks(n, kNnThreads) * (kNnThreads / 32) + far_blocks; }
 
 void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const Rigid& T, double max_range,
                     const int* seed, double* partials, double* out2, const FarWork& fw, cudaStream_t stream) {
@@ -424,9 +448,10 @@ void launch_fitness(const GridView& g, const float4* src, int lo, int hi, const 
   const unsigned nb = nblocks(n, kNnThreads);
   fitness_kernel<false><<<nb, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, seed, partials, 0, fw);
   GICPB_LAUNCHED();
-  fitness_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, seed, partials, (int)nb, fw);
+  const int near_rows = (int)nb * (kNnThreads / 32);
+  fitness_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, src, lo, hi, T, max_range, seed, partials, near_rows, fw);
   GICPB_LAUNCHED();
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb + fw.far_blocks, 2, out2);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, stream>>>(partials, near_rows + fw.far_blocks, 2, out2);
   GICPB_LAUNCHED();
 }
 
@@ -454,7 +479,7 @@ void launch_resolution(const GridView& g, double* partials, double* out2, const 
   GICPB_LAUNCHED();
   resolution_kernel<true><<<fw.far_blocks, kNnThreads, 0, stream>>>(g, partials, (int)nb, fw);
   GICPB_LAUNCHED();
-  reduce_partials_kernel<<<1, 256, 0, stream>>>(partials, (int)nb + fw.far_blocks, 2, out2);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, stream>>>(partials, (int)nb + fw.far_blocks, 2, out2);
   GICPB_LAUNCHED();
 }
 
