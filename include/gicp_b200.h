@@ -106,8 +106,9 @@ int gicpb_comm_rank(const gicpb_ctx* ctx, int* rank, int* world);
  * rank: its window of brick planes, not the whole cloud) and how often a window had to be widened to the whole cloud. */
 int gicpb_shard_info(gicpb_ctx* ctx, int64_t* lo, int64_t* hi, int64_t* n_indexed_here, int64_t* widened);
 /* Optional, after gicpb_comm_init on every rank: fuse the cross-GPU sum of the 14 cost sums INTO the cost kernel over
- * NVLink peer memory (the kernel's last block stores its sums into every rank's slot block, raises a flag, waits for
- * the other ranks' flags and adds the slots in rank order), replacing the ncclAllReduce + copy per evaluation.
+ * NVLink peer memory (the kernel's last block sends its sums into every rank's slot block as self-validating 8-byte
+ * words - half of a double and the evaluation counter - polls the words of the other ranks in its own block and adds
+ * the sums in rank order), replacing the ncclAllReduce + copy per evaluation.
  * gicpb_peer_export returns this rank's cudaIpcMemHandle_t (64 bytes); the caller gathers the handles of all ranks
  * (rank order, 64 bytes each) and passes them to gicpb_peer_import.  All ranks must be processes on one node with
  * peer access between their GPUs; on failure the context keeps using NCCL. */
