@@ -223,6 +223,7 @@ struct gicpb_ctx {
     cudaEvent_t done = nullptr;
     bool pending = false;
     bool sharded = false;    // only this rank's slice of the rows was uploaded: take_prefetch gathers the other ranks'
+    bool gathered = false;   // ... unless do_prefetch already did, on the copy stream (one process per GPU)
     int64_t chunk_rows = 0;  // rows per rank in the gathered buffer (the last rank's slice may be shorter, or empty)
   } prefetch[2];  // 0 target, 1 source
   gicpb_params prm{};
@@ -873,6 +874,15 @@ bool shard_uploads(const gicpb_ctx* c) {
   return enabled && c->world > 1 && (c->local != nullptr || c->comm != nullptr);
 }
 
+// GICPB_GATHER_ON_COPY_STREAM=0: exchange the slices on the compute stream when the cloud is set (measurements)
+bool gather_on_copy_stream() {
+  static const bool enabled = [] {
+    const char* e = std::getenv("GICPB_GATHER_ON_COPY_STREAM");
+    return !(e && *e == '0');
+  }();
+  return enabled;
+}
+
 void gather_slices(gicpb_ctx* c, int which) {
   gicpb_ctx::Prefetch& p = c->prefetch[which];
   const size_t chunk_bytes = (size_t)p.chunk_rows * 12;
@@ -927,6 +937,14 @@ void do_prefetch(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t st
       GICPB_CUDA(cudaMemcpyAsync(p.dev, xyz, (size_t)(n - 1) * stride + 12, cudaMemcpyHostToDevice, c->copy_stream));
     }
   }
+  p.gathered = false;
+  if (p.sharded && !c->local && gather_on_copy_stream()) {
+    // one process per GPU: the slices are exchanged on the copy stream as soon as this rank's has arrived - for the source
+    // that is WHILE the target is indexed on the compute stream, not in front of the source's own index build
+    check_nccl(c, c->nccl->AllGather(p.dev + (size_t)c->rank * (size_t)p.chunk_rows * 12, p.dev, (size_t)p.chunk_rows * 12,
+                                     /*ncclInt8*/ 0, c->comm, c->copy_stream), "ncclAllGather");
+    p.gathered = true;
+  }
   GICPB_CUDA(cudaEventRecord(p.done, c->copy_stream));
   p.host = xyz;
   p.n = n;
@@ -946,7 +964,7 @@ bool take_prefetch(gicpb_ctx* c, int which, const void* xyz, int64_t n, int64_t 
   if (!p.pending) return false;
   p.pending = false;
   GICPB_CUDA(cudaStreamWaitEvent(c->stream, p.done, 0));
-  if (p.sharded) gather_slices(c, which);
+  if (p.sharded && !p.gathered) gather_slices(c, which);
   return true;
 }
 
