@@ -138,6 +138,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // rows in a fixed order (a given input always produces the same bits) and writes `out`.  stamp != 0: `out` is mapped host
 // memory the host polls: the sums travel as stamped 8-byte words (kernels.hpp launch_cost).  kPeer: the sums are first
 // exchanged with the other ranks through peer memory (kernels.hpp PeerReduce).  Must be called by every thread of the block.
+// The arrivals are counted with atomicInc, which wraps to 0 in the very operation of the last block: no reset store that the
+// blocks of the resident kernel's NEXT evaluation would have to see (with the result travelling to the host without a fence
+// nothing would order such a store against it).
 template <int kThreads, bool kPeer>
 __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums], double* __restrict__ partials,
                                                    unsigned* __restrict__ ticket, double* __restrict__ out,
@@ -162,8 +165,8 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(ticket, 1u);
-    is_last = (done == gridDim.x - 1);
+    const unsigned done = atomicInc(ticket, gridDim.x - 1u);
+    is_last = (done == gridDim.x - 1u);
   }
   __syncthreads();
   if (!is_last) return;
@@ -181,7 +184,6 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
 #pragma unroll
     for (int gi = 0; gi < kThreads / 16; ++gi) s += red[gi][threadIdx.x];
   }
-  if (threadIdx.x == 0) *ticket = 0u;
   __shared__ double s_own[kCostSums];
   // stamp != 0: the result goes to the polling host as 28 self-validating 8-byte words (32 bits of a sum | stamp) behind the
   // 16 plain doubles of `out` (kCostOutWords): no fence and no separate flag between the sums and their "ready" mark
