@@ -55,7 +55,7 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[9], double (&v)[9]) {
   }
 }
 
-constexpr int kKnnQueueCap = 12;
+constexpr int kKnnQueueCap = 8;
 
 template <bool kFar, int kKnnThreads>
 __global__ void __launch_bounds__(kKnnThreads) knn_cov_kernel(GridView g, int lo, int hi, int k,
@@ -187,6 +187,7 @@ void launch_knn_covariances(const GridView& g, int lo, int hi, int k, double* no
   if (dev >= 64 || !((attr_set.load() >> dev) & 1ull)) {  // up to 88 KB of dynamic shared memory at k = 32
     GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    GICPB_CUDA(cudaFuncSetAttribute(knn_cov_kernel<false, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (dev < 64) attr_set.fetch_or(1ull << dev);
   }
   if (near_threads == 128)
