@@ -187,8 +187,7 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
   __shared__ double s_own[kCostSums];
   // stamp != 0: the result goes to the polling host as 28 self-validating 8-byte words (32 bits of a sum | stamp) behind the
   // 16 plain doubles of `out` (kCostOutWords): no fence and no separate flag between the sums and their "ready" mark
-  auto publish = [&](bool have) {  // s_own holds the 14 results (written by the threads < kCostSums before a barrier)
-    if (!have) return;
+  auto publish = [&] {  // s_own holds the 14 results (written by the threads < kCostSums before a barrier)
     if (threadIdx.x < 2 * kCostSums) {
       const unsigned long long bits = (unsigned long long)__double_as_longlong(s_own[threadIdx.x >> 1]);
       const unsigned half = (threadIdx.x & 1) ? (unsigned)(bits >> 32) : (unsigned)bits;
@@ -203,7 +202,7 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
     }
     if (threadIdx.x < kCostSums) s_own[threadIdx.x] = s;
     __syncthreads();
-    publish(true);
+    publish();
     return;
   }
   // ---- sum over the ranks through peer memory (kernels.hpp PeerReduce) -------------------------------------------
@@ -256,7 +255,7 @@ __device__ __forceinline__ void reduce_and_publish(const double (&acc)[kCostSums
   }
   if (stamp) {
     __syncthreads();
-    publish(true);
+    publish();
   }
 }
 
