@@ -365,7 +365,7 @@ constexpr int kFarBlocksPerSm = 6;
 FarWork far_work(gicpb_ctx* c, int64_t n_items, int near_rings = kNearMaxRing) {
   c->far_flags.reserve((size_t)std::max<int64_t>(n_items, 1) + kFarTile);
   c->far_counter.reserve(4);
-  return FarWork{c->far_flags.get(), c->far_counter.get(), c->num_sms * kFarBlocksPerSm, near_rings};
+  return FarWork{c->far_flags.get(), c->far_counter.get(), c->num_sms * kFarBlocksPerSm, near_rings, far_tile_for(n_items)};
 }
 
 void update_shard(gicpb_ctx* c) {
